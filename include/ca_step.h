@@ -1,0 +1,199 @@
+/*
+ * ca_step.h — C-ABI of libcastep.so, the B200-native (sm_100a) vectorised replacement of the
+ * reference's env.step() hot path.  Plain pointers and sizes only; no torch types.
+ *
+ * What each entry point replaces in mit-acl/rl_collision_avoidance (paths under /root/reference,
+ * GCA = gym-collision-avoidance/gym_collision_avoidance, GA3C = ga3c/GA3C):
+ *
+ *   ca_create / ca_destroy     CollisionAvoidanceEnv.__init__           GCA/envs/collision_avoidance_env.py:41-129
+ *                              (+ the Config values it reads            GCA/envs/config.py:30-47,64-76,171)
+ *   ca_set_world_state         CollisionAvoidanceEnv.set_agents         GCA/envs/collision_avoidance_env.py:260-268
+ *                              + Agent.__init__/Agent.reset             GCA/envs/agent.py:29-136
+ *   ca_reset                   CollisionAvoidanceEnv.reset              GCA/envs/collision_avoidance_env.py:196-215
+ *   ca_step / ca_step_host     CollisionAvoidanceEnv.step               GCA/envs/collision_avoidance_env.py:131-194
+ *                                _take_action                           :217-252
+ *                                Agent.take_action                      GCA/envs/agent.py:190-238
+ *                                UnicycleDynamics.step                  GCA/envs/dynamics/UnicycleDynamics.py:14-47
+ *                                Dynamics.update_ego_frame              GCA/envs/dynamics/Dynamics.py:24-41
+ *                                _compute_rewards/_check_for_collisions GCA/envs/collision_avoidance_env.py:319-409
+ *                                OtherAgentsStatesSensor.sense          GCA/envs/sensors/OtherAgentsStatesSensor.py:20-144
+ *                                MultiagentDictToMultiagentArrayWrapper GCA/envs/wrappers.py:111-139
+ *                                _check_which_agents_done               GCA/envs/collision_avoidance_env.py:411-439
+ *                              and, with auto_reset, DummyVecEnv.step_wait (openai/baselines@ea25b9e, not vendored)
+ *   ca_get_state               reading Agent attributes                 GCA/envs/agent.py:66-136
+ *   ca_nstep_returns           ProcessAgent._accumulate_rewards         GA3C/ProcessAgent.py:54-79
+ *
+ * Conventions
+ *   - every function returns 0 (CA_OK) or a negative ca_status; nothing throws across the ABI;
+ *     ca_strerror(code) names the code, ca_last_error() gives the last detailed message (thread local).
+ *   - the library owns the internal state arrays; the caller owns every I/O buffer and the stream.
+ *   - a handle is bound to one CUDA device; calls on one handle must be serialised by the caller;
+ *     device-pointer entry points are asynchronous (stream ordered); distinct handles are independent.
+ *   - `stream` is a cudaStream_t passed as void* (NULL = the legacy default stream).
+ *   - there is NO CPU fallback: without a usable CUDA device ca_create fails with CA_ERR_CUDA.
+ */
+#ifndef CA_STEP_H_
+#define CA_STEP_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CA_ABI_VERSION 1
+
+/* hard limit: one world's agents live in the lanes of one warp */
+#define CA_MAX_AGENTS 32
+
+/* status codes */
+typedef enum ca_status {
+  CA_OK = 0,
+  CA_ERR_INVALID_ARG = -1,
+  CA_ERR_CUDA = -2,
+  CA_ERR_NOT_INITIALISED = -3, /* step/reset before ca_set_world_state */
+  CA_ERR_UNSUPPORTED = -4,
+  CA_ERR_ALLOC = -5
+} ca_status;
+
+/* AGENT_SORTING_METHOD, GCA/envs/config.py:169-172 */
+typedef enum ca_sort_method {
+  CA_SORT_CLOSEST_FIRST = 0,
+  CA_SORT_CLOSEST_LAST = 1,
+  CA_SORT_TIME_TO_IMPACT = 2
+} ca_sort_method;
+
+/* game_over rule, GCA/envs/collision_avoidance_env.py:427-437 */
+typedef enum ca_game_over_mode {
+  CA_OVER_ALL_LEARNING_DONE = 0, /* training (default) */
+  CA_OVER_ALL_DONE = 1,          /* Config.EVALUATE_MODE */
+  CA_OVER_FIRST_AGENT_DONE = 2   /* Config.TRAIN_SINGLE_AGENT */
+} ca_game_over_mode;
+
+/* per-agent policy type (what acts inside step), GCA/envs/test_cases.py:48-58 */
+typedef enum ca_policy {
+  CA_POLICY_LEARNING_GA3C = 0, /* external, discrete action 0..10    policies/LearningPolicyGA3C.py:13-27 */
+  CA_POLICY_NONCOOP = 1,       /* internal                           policies/NonCooperativePolicy.py:9-22 */
+  CA_POLICY_STATIC = 2,        /* internal, goal := pos              policies/StaticPolicy.py:9-23 */
+  CA_POLICY_LEARNING = 3       /* external, continuous [speed_frac, heading_frac]  policies/LearningPolicy.py:13-33 */
+} ca_policy;
+
+/* agent flag bits (state column CA_S_FLAGS, and the bits of the `done` output's source) */
+#define CA_F_AT_GOAL 1u              /* Agent.is_at_goal */
+#define CA_F_WAS_AT_GOAL 2u          /* Agent.was_at_goal_already */
+#define CA_F_IN_COLLISION 4u         /* Agent.in_collision */
+#define CA_F_WAS_IN_COLLISION 8u     /* Agent.was_in_collision_already */
+#define CA_F_RAN_OUT_OF_TIME 16u     /* Agent.ran_out_of_time */
+#define CA_F_DONE_MASK (CA_F_AT_GOAL | CA_F_IN_COLLISION | CA_F_RAN_OUT_OF_TIME)
+
+/* columns of the `init` tensor of ca_set_world_state: double[W][A][CA_INIT_STRIDE] */
+enum {
+  CA_I_PX = 0, CA_I_PY, CA_I_GX, CA_I_GY, CA_I_PREF_SPEED, CA_I_RADIUS, CA_I_HEADING, CA_I_POLICY,
+  CA_I_TIME_REMAINING, /* Agent.time_remaining_to_reach_goal at reset; NaN => library computes
+                          max(max_time_ratio*(|p-g|-near_goal_threshold)/pref_speed, dt)  (agent.py:98-103) */
+  CA_I_RESERVED,
+  CA_INIT_STRIDE
+};
+
+/* columns of ca_get_state: double[W][A][CA_STATE_STRIDE] */
+enum {
+  CA_S_PX = 0, CA_S_PY, CA_S_HEADING, CA_S_VX, CA_S_VY, CA_S_TIME_REMAINING, CA_S_GX, CA_S_GY,
+  CA_S_RADIUS, CA_S_PREF_SPEED, CA_S_FLAGS, CA_S_POLICY,
+  CA_STATE_STRIDE
+};
+
+/* Observation row (float32), order = Config.STATES_IN_OBS of GA3C/Config.py:40, flattened like
+ * GCA/envs/wrappers.py:115-139:  [is_learning, num_other_agents, dist_to_goal, heading_ego_frame,
+ * pref_speed, radius, M x (p_prll, p_orth, v_prll, v_orth, other_radius, combined_radius, dist_2_other)]
+ * L = 6 + 7*M.  Rows of absent agents and unused other-slots are zero. */
+#define CA_OBS_HOST_LEN 6
+#define CA_OBS_OTHER_LEN 7
+#define CA_OBS_LEN(M) (CA_OBS_HOST_LEN + CA_OBS_OTHER_LEN * (M))
+
+typedef struct ca_config {
+  int32_t abi_version;          /* must be CA_ABI_VERSION */
+  int32_t num_worlds;           /* W: independent environments advanced per launch */
+  int32_t max_agents;           /* A: Config.MAX_NUM_AGENTS_IN_ENVIRONMENT, 1..CA_MAX_AGENTS */
+  int32_t max_others_observed;  /* M: Config.MAX_NUM_OTHER_AGENTS_OBSERVED, 1..A-1 (>=1) */
+  int32_t sort_method;          /* ca_sort_method */
+  int32_t game_over_mode;       /* ca_game_over_mode */
+  int32_t auto_reset;           /* 1: on game_over a world reloads its injected initial state inside the same
+                                   launch and `obs` carries the NEW episode's first observation while
+                                   reward/done/game_over describe the finished step (DummyVecEnv semantics) */
+  int32_t device;               /* CUDA device ordinal */
+  double dt;                    /* Config.DT */
+  double near_goal_threshold;   /* Config.NEAR_GOAL_THRESHOLD */
+  double getting_close_range;   /* Config.GETTING_CLOSE_RANGE */
+  double reward_at_goal;        /* Config.REWARD_AT_GOAL */
+  double reward_collision_with_agent; /* Config.REWARD_COLLISION_WITH_AGENT */
+  double reward_time_step;      /* Config.REWARD_TIME_STEP */
+  double min_possible_reward;   /* clip bounds, collision_avoidance_env.py:463-483 */
+  double max_possible_reward;
+  double max_time_ratio;        /* Config.MAX_TIME_RATIO (only used when CA_I_TIME_REMAINING is NaN) */
+  double max_heading_change;    /* env.max_heading_change = pi/3 (continuous LearningPolicy only) */
+  double sensing_horizon;       /* Config.SENSING_HORIZON (inf) */
+} ca_config;
+
+typedef struct ca_env ca_env;
+
+/* Fill *cfg with the reference's default training configuration (GCA/envs/config.py) for W worlds of A agents. */
+int ca_default_config(ca_config* cfg, int32_t num_worlds, int32_t max_agents);
+
+int ca_create(const ca_config* cfg, ca_env** out);
+int ca_destroy(ca_env* env);
+
+/* Inject the initial configuration of every world (≙ env.set_agents + Agent.__init__) and reset.
+ * init: double[W][A][CA_INIT_STRIDE]; num_agents: int32[W] with 1 <= n_w <= A (rows >= n_w ignored).
+ * on_device != 0: both pointers are device pointers (copied stream-ordered on `stream`). */
+int ca_set_world_state(ca_env* env, const double* init, const int32_t* num_agents, int on_device, void* stream);
+
+/* Reset worlds to their injected initial state (world_mask: device uint8[W], NULL = all) and write the
+ * first observation of every world (unmasked worlds: their current observation) to obs (device float[W][A][L]);
+ * sorted_idx (device int32[W][A][M], may be NULL) receives the neighbour order (-1 = empty slot). */
+int ca_reset(ca_env* env, const uint8_t* world_mask, float* obs, int32_t* sorted_idx, void* stream);
+
+/* Advance every world one time step.  All pointers are DEVICE pointers.
+ *   actions      int32[W][A]      discrete action 0..10 per CA_POLICY_LEARNING_GA3C agent (others ignored)
+ *   cont_actions double[W][A][2]  [speed_frac, heading_frac] per CA_POLICY_LEARNING agent; NULL = every such
+ *                                 agent gets the no-op command [0, 0.5] (zero speed, zero heading change)
+ *   obs          float[W][A][L]   next observation
+ *   reward       float[W][A]      0 for absent agents
+ *   done         uint8[W][A]      which_agents_done; 1 for absent agents
+ *   game_over    uint8[W]
+ *   sorted_idx   int32[W][A][M]   optional (NULL to skip): indices chosen by the sensor, -1 = empty slot */
+int ca_step(ca_env* env, const int32_t* actions, const double* cont_actions, float* obs, float* reward,
+            uint8_t* done, uint8_t* game_over, int32_t* sorted_idx, void* stream);
+
+/* Same step through HOST buffers (what a host-side env.step() caller sees): copies actions host->device,
+ * launches, copies obs/reward/done/game_over device->host and synchronises.  Buffers registered with
+ * cudaHostRegister / allocated pinned make the copies asynchronous DMA; pageable memory also works. */
+int ca_step_host(ca_env* env, const int32_t* actions, const double* cont_actions, float* obs, float* reward,
+                 uint8_t* done, uint8_t* game_over, int32_t* sorted_idx);
+
+/* Copy the full agent state out: double[W][A][CA_STATE_STRIDE] (device pointer if on_device, else host; host
+ * copies synchronise). */
+int ca_get_state(ca_env* env, double* out, int on_device, void* stream);
+
+/* Number of kernels this handle has launched since creation (bench.py's gpu_launches). */
+int ca_launch_count(const ca_env* env, int64_t* out);
+
+/* Timing helper for bench.py: CUDA-event time (ms) of `iters` back-to-back ca_step launches on an internal
+ * stream with the given device buffers (events recorded on the launching stream). */
+int ca_time_steps(ca_env* env, const int32_t* actions, float* obs, float* reward, uint8_t* done,
+                  uint8_t* game_over, int iters, float* ms_out);
+
+/* n-step discounted returns over a rollout segment (≙ ProcessAgent._accumulate_rewards, GA3C/ProcessAgent.py:54-79),
+ * batched over N independent agent streams, device pointers:
+ *   reward  float[T][N], bootstrap float[N] (terminal_reward: V(s_T) or 0 when done), out float[T][N]
+ *   out[t] = reward[t] + gamma * out[t+1], out[T] := bootstrap. */
+int ca_nstep_returns(const float* reward, const float* bootstrap, float* out, int32_t T, int32_t N,
+                     float gamma, int device, void* stream);
+
+const char* ca_strerror(int code);
+const char* ca_last_error(void);
+int ca_abi_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CA_STEP_H_ */
