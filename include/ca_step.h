@@ -170,6 +170,9 @@ int ca_step(ca_env* env, const int32_t* actions, const double* cont_actions, flo
 int ca_step_host(ca_env* env, const int32_t* actions, const double* cont_actions, float* obs, float* reward,
                  uint8_t* done, uint8_t* game_over, int32_t* sorted_idx);
 
+/* ca_reset through HOST buffers (world_mask host uint8[W] or NULL; obs/sorted_idx host, sorted_idx may be NULL). */
+int ca_reset_host(ca_env* env, const uint8_t* world_mask, float* obs, int32_t* sorted_idx);
+
 /* Copy the full agent state out: double[W][A][CA_STATE_STRIDE] (device pointer if on_device, else host; host
  * copies synchronise). */
 int ca_get_state(ca_env* env, double* out, int on_device, void* stream);
@@ -177,10 +180,10 @@ int ca_get_state(ca_env* env, double* out, int on_device, void* stream);
 /* Number of kernels this handle has launched since creation (bench.py's gpu_launches). */
 int ca_launch_count(const ca_env* env, int64_t* out);
 
-/* Timing helper for bench.py: CUDA-event time (ms) of `iters` back-to-back ca_step launches on an internal
- * stream with the given device buffers (events recorded on the launching stream). */
-int ca_time_steps(ca_env* env, const int32_t* actions, float* obs, float* reward, uint8_t* done,
-                  uint8_t* game_over, int iters, float* ms_out);
+/* Pinned (page-locked) host memory for the *_host entry points, so that a ctypes/cgo caller gets
+ * asynchronous DMA copies without depending on another CUDA binding. */
+int ca_host_alloc(void** out, uint64_t bytes);
+int ca_host_free(void* ptr);
 
 /* n-step discounted returns over a rollout segment (≙ ProcessAgent._accumulate_rewards, GA3C/ProcessAgent.py:54-79),
  * batched over N independent agent streams, device pointers:

@@ -1,0 +1,483 @@
+// ca_kernels.cuh — the fused env.step() kernel for sm_100a.
+//
+// One launch advances every world one time step (reference: CollisionAvoidanceEnv.step,
+// GCA/envs/collision_avoidance_env.py:131-194).  Mapping: lane = agent; a warp carries
+// floor(32 / A) whole worlds in consecutive lane groups, so the flat (world, agent) index of a lane is
+// first_world_of_warp * A + lane and every SoA state array is read/written as one contiguous,
+// fully coalesced run per warp.  Other agents' states are fetched with warp shuffles inside the lane
+// group (all-pairs distance), the neighbour order is a stable rank-by-counting over per-lane keys
+// held in shared memory, and the observation rows are assembled in a shared-memory tile that the CTA
+// writes out as one contiguous block (TMA bulk store cp.async.bulk.global.shared::cta when the tile is
+// 16-byte aligned, else coalesced scalar stores).
+//
+// Numerics: state and every decision (collision d <= R, goal test, time-out,
+// sort keys) are IEEE float64 computed with the same operation order as the reference's Python
+// float64 arithmetic; the file is compiled with -fmad=false so nvcc never contracts a*b+c, and the
+// places where NumPy itself fuses (np.dot on 2-vectors) use __fma_rn explicitly.  Only the commanded
+// [speed, dheading] is rounded to float32 (collision_avoidance_env.py:238) and outputs are float32.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/ca_step.h"
+
+namespace ca {
+
+constexpr int kBlock = 128;           // threads per CTA
+constexpr int kWarps = kBlock / 32;   // warps per CTA
+constexpr unsigned kFull = 0xffffffffu;
+constexpr double kPi = 3.141592653589793;  // np.pi
+
+struct StateArrays {
+  double *px, *py, *hd, *vx, *vy, *tr, *gx, *gy, *rad, *ps;  // [W*A] each
+  uint8_t *flags, *policy;                                     // [W*A]
+};
+
+struct Params {
+  int W, A, M, L, wpw;  // wpw = worlds per warp = 32 / A
+  int sort_method, over_mode, auto_reset;
+  int tile_floats;      // floats in the CTA's obs tile = kWarps * wpw * A * L
+  int use_bulk_store;   // 1: TMA bulk store of full tiles
+  double dt, thr_sq, close_range, r_goal, r_coll, r_step, r_min, r_max, max_heading_change, sensing_horizon;
+  StateArrays s;        // live state
+  StateArrays s0;       // snapshot injected by ca_set_world_state (for reset)
+  const int32_t* nag;   // [W]
+  // I/O (device)
+  const int32_t* actions;  // [W*A]
+  const double* cont;      // [W*A*2] or null
+  const uint8_t* mask;     // reset kernel: [W] or null (= all)
+  float* obs;              // [W*A*L]
+  float* reward;           // [W*A]
+  uint8_t* done;           // [W*A]
+  uint8_t* over;           // [W]
+  int32_t* sidx;           // [W*A*M] or null
+};
+
+// Actions table, GCA/envs/policies/GA3C_CADRL/network.py:13-16 (values of the reference's np.mgrid expression)
+__constant__ double kActSpeed[11] = {1.0, 1.0, 1.0, 1.0, 1.0, 0.5, 0.5, 0.5, 0.0, 0.0, 0.0};
+__constant__ double kActDhead[11] = {-0x1.0c152382d7365p-1, -0x1.0c152382d7365p-2, 0.0, 0x1.0c152382d7366p-2,
+                                     0x1.0c152382d7365p-1,  -0x1.0c152382d7365p-1, 0.0, 0x1.0c152382d7365p-1,
+                                     -0x1.0c152382d7365p-1, 0.0,                   0x1.0c152382d7365p-1};
+
+// GCA/envs/util.py:132-137 (same loops; non-finite input is left alone instead of spinning forever)
+__device__ __forceinline__ double wrap_angle(double a) {
+  if (!isfinite(a)) return a;
+  while (a >= kPi) a -= 2 * kPi;
+  while (a < -kPi) a += 2 * kPi;
+  return a;
+}
+
+// np.dot on 2-vectors as NumPy/OpenBLAS evaluates it: fma(a1, b1, a0*b0) (see oracle/ca_oracle.c np_dot2)
+__device__ __forceinline__ double dot2(double a0, double a1, double b0, double b1) {
+  return __fma_rn(a1, b1, __dmul_rn(a0, b0));
+}
+
+struct Ego {
+  double dist, hego, prx, pry;  // orth = (-pry, prx)
+};
+
+// Agent.get_ref (GCA/envs/agent.py:326-346) + Dynamics.update_ego_frame (GCA/envs/dynamics/Dynamics.py:24-41)
+__device__ __forceinline__ Ego ego_frame(double px, double py, double gx, double gy, double hd) {
+  Ego e;
+  const double dx = gx - px, dy = gy - py;
+  e.dist = sqrt(dx * dx + dy * dy);
+  if (e.dist > 1e-8) {
+    e.prx = dx / e.dist;
+    e.pry = dy / e.dist;
+  } else {
+    e.prx = dx;
+    e.pry = dy;
+  }
+  e.hego = wrap_angle(hd - atan2(e.pry, e.prx));
+  return e;
+}
+
+__device__ __forceinline__ double shfl_d(double v, int src) { return __shfl_sync(kFull, v, src); }
+
+// compute_time_to_impact, GCA/envs/util.py:14-104 (host pos/vel, other pos/vel, combined radius)
+__device__ double time_to_impact(double hx, double hy, double hvx, double hvy, double ox, double oy, double ovx,
+                                 double ovy, double r) {
+  const double v0 = hvx - ovx, v1 = hvy - ovy;
+  const double ex = hx - ox, ey = hy - oy;
+  const double sqd = ex * ex + ey * ey - r * r;
+  if (sqd < 0) return 0.0;
+  const double sqrt_term = sqrt(sqd);
+  const double xnum1 = r * r * ex, xnum2 = r * ey * sqrt_term;
+  const double ynum1 = r * r * ey, ynum2 = r * ex * sqrt_term;
+  const double den = ex * ex + ey * ey;
+  const double c1x = ((xnum1 + xnum2) / den + ox) - hx, c1y = ((ynum1 - ynum2) / den + oy) - hy;
+  const double c2x = ((xnum1 - xnum2) / den + ox) - hx, c2y = ((ynum1 + ynum2) / den + oy) - hy;
+  const double c1v = c1x * v1 - c1y * v0, c12 = c1x * c2y - c1y * c2x;
+  const double c2v = c2x * v1 - c2y * v0, c21 = c2x * c1y - c2y * c1x;
+  if (!(c1v * c12 >= 0 && c2v * c21 >= 0)) return INFINITY;
+  if (fabs(v0) < 1e-5 && fabs(v1) < 1e-5) return INFINITY;
+  double x1, x2, y1, y2;
+  if (fabs(v0) < 1e-5) {
+    x1 = x2 = hx;
+    const double B = -2 * oy, C = oy * oy + (hx - ox) * (hx - ox) - r * r;
+    const double disc = sqrt(B * B - 4 * C);
+    y1 = (-B + disc) / 2;
+    y2 = (-B - disc) / 2;
+  } else {
+    const double m = v1 / v0;
+    const double Aq = 1 + m * m;
+    const double B = -2 * ox + 2 * m * (hy - oy - m * hx);
+    const double t = m * hx - (hy - oy);
+    const double C = ox * ox - r * r + t * t;
+    const double disc = sqrt(B * B - 4 * Aq * C);
+    x1 = (-B + disc) / (2 * Aq);
+    x2 = (-B - disc) / (2 * Aq);
+    y1 = m * (x1 - hx) + hy;
+    y2 = m * (x2 - hx) + hy;
+  }
+  const double d1 = sqrt(dot2(x1 - hx, y1 - hy, x1 - hx, y1 - hy));
+  const double d2 = sqrt(dot2(x2 - hx, y2 - hy, x2 - hx, y2 - hy));
+  const double d = (d2 < d1) ? d2 : d1;
+  return d / sqrt(dot2(v0, v1, v0, v1));
+}
+
+// Strict "sorts before" on the sensor's keys (OtherAgentsStatesSensor.get_clipped_sorted_inds,
+// GCA/envs/sensors/OtherAgentsStatesSensor.py:20-55) with the list position (= agent index) as the
+// final tiebreak, which is what Python's stable sorted() amounts to.  q = rint(100*dist_2_other) orders
+// exactly like round(dist_2_other, 2) (division by 100 is monotone and injective on these integers).
+//   mode 0: (q, p_orth)    mode 1: (-q, p_orth)    mode 2: (-tti, -q, p_orth)
+__device__ __forceinline__ bool key_before(int mode, double qa, double pa, double ta, int ia, double qb, double pb,
+                                           double tb, int ib) {
+  const bool tail = (pa < pb) || (pa == pb && ia < ib);
+  if (mode == 0) return (qa < qb) || (qa == qb && tail);
+  const bool qtail = (qa > qb) || (qa == qb && tail);
+  if (mode == 1) return qtail;
+  return (ta > tb) || (ta == tb && qtail);
+}
+
+// The per-lane agent record kept in registers.
+struct Agent {
+  double px, py, hd, vx, vy, tr, gx, gy, rad, ps;
+  unsigned flags;
+  int policy;
+};
+
+__device__ __forceinline__ void load_agent(const StateArrays& s, size_t g, Agent& a) {
+  a.px = s.px[g]; a.py = s.py[g]; a.hd = s.hd[g]; a.vx = s.vx[g]; a.vy = s.vy[g]; a.tr = s.tr[g];
+  a.gx = s.gx[g]; a.gy = s.gy[g]; a.rad = s.rad[g]; a.ps = s.ps[g];
+  a.flags = s.flags[g]; a.policy = s.policy[g];
+}
+
+__device__ __forceinline__ void zero_agent(Agent& a) {
+  a.px = a.py = a.hd = a.vx = a.vy = a.tr = a.gx = a.gy = a.rad = a.ps = 0.0;
+  a.flags = 0; a.policy = 0;
+}
+
+// Shared-memory carve-up of one CTA.
+struct Smem {
+  float* tile;   // [kWarps*wpw][A][L] observation rows of this CTA's worlds
+  double* kq;    // [A][kBlock] rint(100 * dist_2_other) of (lane, other j)
+  double* kp;    // [A][kBlock] p_orth
+  double* kd;    // [A][kBlock] centre distance
+  double* kt;    // [A][kBlock] time to impact (only with CA_SORT_TIME_TO_IMPACT)
+};
+
+// All-pairs pass for the lane's agent i against every j of its world:
+//   kCollide: collision flag and nearest gap (CollisionAvoidanceEnv._check_for_collisions, :370-409)
+//   always:   sensor keys into shared memory (OtherAgentsStatesSensor.sense first loop, :72-103)
+template <bool kCollide>
+__device__ __forceinline__ void pair_pass(const Params& p, const Smem& sm, const Agent& a, const Ego& e, bool valid,
+                                          int n, int i, int base, int tid, bool& coll, double& nearest) {
+  coll = false;
+  nearest = INFINITY;
+  for (int j = 0; j < p.A; ++j) {
+    const int src = (base + j) & 31;
+    const double xj = shfl_d(a.px, src), yj = shfl_d(a.py, src), rj = shfl_d(a.rad, src);
+    double vxj = 0, vyj = 0;
+    if (p.sort_method == CA_SORT_TIME_TO_IMPACT) { vxj = shfl_d(a.vx, src); vyj = shfl_d(a.vy, src); }
+    if (valid && j < n && j != i) {
+      const double rx = xj - a.px, ry = yj - a.py;
+      const double d = sqrt(rx * rx + ry * ry);  // l2norm / vec2_l2_norm (util.py:8-12,106-112)
+      if (kCollide) {
+        const double R = a.rad + rj;
+        if (d <= R) coll = true;
+        if (j > i) nearest = fmin(nearest, d - R);  // only the lower index is updated (:393)
+      }
+      const double d2o = d - a.rad - rj;
+      const int at = j * kBlock + tid;
+      sm.kq[at] = rint(d2o * 100.0);
+      sm.kp[at] = dot2(rx, ry, -e.pry, e.prx);
+      sm.kd[at] = d;
+      if (p.sort_method == CA_SORT_TIME_TO_IMPACT)
+        sm.kt[at] = time_to_impact(a.px, a.py, a.vx, a.vy, xj, yj, vxj, vyj, a.rad + rj);
+    }
+  }
+}
+
+// Rank the others, clip to M, order per sort method and write the lane's observation row into the tile
+// (OtherAgentsStatesSensor.sense second loop :105-144; dense row of GCA/envs/wrappers.py:130-139).
+__device__ __forceinline__ void write_obs_row(const Params& p, const Smem& sm, const Agent& a, const Ego& e,
+                                              bool world_ok, bool valid, int n, int i, int base, int tid,
+                                              float* row, int32_t* sidx_row) {
+  const int M = p.M;
+  const bool tti = p.sort_method == CA_SORT_TIME_TO_IMPACT;
+  const int mode1 = tti ? 2 : 0;                                   // key of the first (clipping) sort
+  const int mode2 = p.sort_method == CA_SORT_CLOSEST_LAST ? 1 : mode1;  // key of the final order
+  const bool horizon = isfinite(p.sensing_horizon);
+  // candidates: others inside the sensing horizon (config.py:76, sensor :92-94)
+  unsigned cand = 0;
+  if (valid)
+    for (int j = 0; j < n; ++j)
+      if (j != i && !(horizon && sm.kd[j * kBlock + tid] > p.sensing_horizon)) cand |= 1u << j;
+  int count = __popc(cand);
+  unsigned sel = cand;
+  const bool clip = count > M;
+  if (clip) {  // first sort + clip to the M closest
+    sel = 0;
+    for (int j = 0; j < n; ++j) {
+      if (!((cand >> j) & 1u)) continue;
+      const int aj = j * kBlock + tid;
+      const double qj = sm.kq[aj], pj = sm.kp[aj], tj = tti ? sm.kt[aj] : 0.0;
+      int rank = 0;
+      for (int k = 0; k < n; ++k) {
+        if (k == j || !((cand >> k) & 1u)) continue;
+        const int ak = k * kBlock + tid;
+        rank += key_before(mode1, sm.kq[ak], sm.kp[ak], tti ? sm.kt[ak] : 0.0, k, qj, pj, tj, j) ? 1 : 0;
+      }
+      if (rank < M) sel |= 1u << j;
+    }
+    count = M;
+  }
+  if (world_ok) {
+    if (valid) {
+      row[0] = (a.policy == CA_POLICY_LEARNING_GA3C || a.policy == CA_POLICY_LEARNING) ? 1.f : 0.f;
+      row[1] = (float)count;
+      row[2] = (float)e.dist;
+      row[3] = (float)e.hego;
+      row[4] = (float)a.ps;
+      row[5] = (float)a.rad;
+      for (int q = CA_OBS_HOST_LEN + CA_OBS_OTHER_LEN * count; q < p.L; ++q) row[q] = 0.f;
+      if (sidx_row) for (int k = count; k < M; ++k) sidx_row[k] = -1;
+    } else {
+      for (int q = 0; q < p.L; ++q) row[q] = 0.f;
+      if (sidx_row) for (int k = 0; k < M; ++k) sidx_row[k] = -1;
+    }
+  }
+  // second loop: every lane takes part in the shuffles, selected others land in their slot
+  for (int j = 0; j < p.A; ++j) {
+    const int src = (base + j) & 31;
+    const double xj = shfl_d(a.px, src), yj = shfl_d(a.py, src), rj = shfl_d(a.rad, src);
+    const double vxj = shfl_d(a.vx, src), vyj = shfl_d(a.vy, src);
+    if (!((sel >> j) & 1u)) continue;
+    const int aj = j * kBlock + tid;
+    const double qj = sm.kq[aj], pj = sm.kp[aj], tj = tti ? sm.kt[aj] : 0.0;
+    int slot = 0;
+    for (int k = 0; k < n; ++k) {
+      if (k == j || !((sel >> k) & 1u)) continue;
+      const int ak = k * kBlock + tid;
+      slot += key_before(mode2, sm.kq[ak], sm.kp[ak], tti ? sm.kt[ak] : 0.0, k, qj, pj, tj, j) ? 1 : 0;
+    }
+    const double rx = xj - a.px, ry = yj - a.py;
+    float* s = row + CA_OBS_HOST_LEN + CA_OBS_OTHER_LEN * slot;
+    s[0] = (float)dot2(rx, ry, e.prx, e.pry);
+    s[1] = (float)pj;
+    s[2] = (float)dot2(vxj, vyj, e.prx, e.pry);
+    s[3] = (float)dot2(vxj, vyj, -e.pry, e.prx);
+    s[4] = (float)rj;
+    s[5] = (float)(a.rad + rj);
+    s[6] = (float)(sm.kd[aj] - a.rad - rj);
+    if (sidx_row) sidx_row[slot] = j;
+  }
+}
+
+__device__ __forceinline__ uint32_t smem_u32(const void* ptr) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(ptr));
+}
+
+// CTA-wide copy of the observation tile to global memory.
+__device__ __forceinline__ void store_tile(const Params& p, const float* tile, long first_world, int tid) {
+  const long worlds_left = (long)p.W - first_world;
+  if (worlds_left <= 0) return;
+  const int tile_worlds = kWarps * p.wpw;
+  const int nw = worlds_left < tile_worlds ? (int)worlds_left : tile_worlds;
+  const int nfloats = nw * p.A * p.L;
+  float* dst = p.obs + (size_t)first_world * p.A * p.L;
+  if (p.use_bulk_store && nw == tile_worlds) {
+    // TMA bulk store (UBLKCP): generic-proxy writes to smem must be made visible to the async proxy first
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+    if (tid == 0) {
+      asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(tile)),
+                   "r"(nfloats * 4)
+                   : "memory");
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    }
+    return;
+  }
+  __syncthreads();
+  for (int q = tid; q < nfloats; q += kBlock) dst[q] = tile[q];
+}
+
+template <bool kStep>
+__global__ void __launch_bounds__(kBlock) ca_world_kernel(const __grid_constant__ Params p) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  Smem sm;
+  sm.tile = reinterpret_cast<float*>(smem_raw);
+  const int tile_bytes = ((p.tile_floats * 4 + 127) / 128) * 128;
+  sm.kq = reinterpret_cast<double*>(smem_raw + tile_bytes);
+  sm.kp = sm.kq + p.A * kBlock;
+  sm.kd = sm.kp + p.A * kBlock;
+  sm.kt = sm.kd + p.A * kBlock;
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int A = p.A;
+  const int wl = lane / A;      // world slot inside the warp
+  const int i = lane - wl * A;  // agent index inside the world
+  const int base = wl * A;      // first lane of the world's group
+  const long first_world_cta = (long)blockIdx.x * kWarps * p.wpw;
+  const long w = first_world_cta + (long)warp * p.wpw + wl;
+  const bool world_ok = wl < p.wpw && w < p.W;
+  const int n = world_ok ? p.nag[w] : 0;
+  const bool valid = world_ok && i < n;
+  const size_t g = world_ok ? (size_t)w * A + i : 0;
+  const unsigned gmask = (A >= 32 ? kFull : ((1u << A) - 1u)) << (base & 31);
+
+  float* row = sm.tile + ((size_t)(warp * p.wpw + wl) * A + i) * p.L;
+  int32_t* sidx_row = (p.sidx && world_ok) ? p.sidx + g * p.M : nullptr;
+
+  Agent a;
+  if (valid) load_agent(p.s, g, a); else zero_agent(a);
+
+  bool do_reset;  // world reloads its injected initial state
+  if (kStep) {
+    // ---- _take_action (:217-252): every agent picks its command first ...
+    const bool was_done = (a.flags & CA_F_DONE_MASK) != 0;
+    float cmd_speed = 0.f, cmd_dh = 0.f;  // all_actions is float32 (:238)
+    if (valid && !was_done) {
+      if (a.policy == CA_POLICY_NONCOOP) {
+        // NonCooperativePolicy.find_next_action (policies/NonCooperativePolicy.py:9-22) reads the ego
+        // heading of the pre-step state
+        const Ego e0 = ego_frame(a.px, a.py, a.gx, a.gy, a.hd);
+        cmd_speed = (float)a.ps;
+        cmd_dh = (float)(-e0.hego);
+      } else if (a.policy == CA_POLICY_LEARNING_GA3C) {  // LearningPolicyGA3C.external_action_to_action
+        int k = p.actions[g];
+        k = k < 0 ? 0 : (k > 10 ? 10 : k);
+        cmd_speed = (float)(a.ps * kActSpeed[k]);
+        cmd_dh = (float)kActDhead[k];
+      } else if (a.policy == CA_POLICY_LEARNING) {  // LearningPolicy.external_action_to_action
+        double e0 = 0.0, e1 = 0.5;
+        if (p.cont) { e0 = p.cont[2 * g]; e1 = p.cont[2 * g + 1]; }
+        cmd_speed = (float)(a.ps * e0);
+        cmd_dh = (float)(p.max_heading_change * (2. * e1 - 1.));
+      } else if (a.policy == CA_POLICY_STATIC) {  // StaticPolicy: goal := pos
+        a.gx = a.px;
+        a.gy = a.py;
+      }
+    }
+    // ---- ... then all agents move (Agent.take_action, agent.py:190-238)
+    if (valid) {
+      if (was_done) {
+        if (a.flags & CA_F_AT_GOAL) a.flags |= CA_F_WAS_AT_GOAL;
+        if (a.flags & CA_F_IN_COLLISION) a.flags |= CA_F_WAS_IN_COLLISION;
+        a.vx = 0.0;
+        a.vy = 0.0;
+      } else {
+        // UnicycleDynamics.step (dynamics/UnicycleDynamics.py:14-47)
+        const double speed = (double)cmd_speed;
+        const double h = wrap_angle((double)cmd_dh + a.hd);
+        double sh, ch;
+        sincos(h, &sh, &ch);
+        a.px += speed * ch * p.dt;
+        a.py += speed * sh * p.dt;
+        a.vx = speed * ch;
+        a.vy = speed * sh;
+        a.hd = h;
+        const double ex = a.px - a.gx, ey = a.py - a.gy;  // _check_if_at_goal (agent.py:148-151)
+        if (ex * ex + ey * ey <= p.thr_sq) a.flags |= CA_F_AT_GOAL; else a.flags &= ~CA_F_AT_GOAL;
+        a.tr -= p.dt;  // agent.py:232-236
+        if (a.tr <= 0.0) a.flags |= CA_F_RAN_OUT_OF_TIME;
+      }
+    }
+  }
+
+  Ego e = ego_frame(a.px, a.py, a.gx, a.gy, a.hd);
+
+  if (kStep) {
+    bool coll;
+    double nearest;
+    pair_pass<true>(p, sm, a, e, valid, n, i, base, tid, coll, nearest);
+    // ---- _compute_rewards (:319-368)
+    double r = p.r_step;
+    if (valid) {
+      if (a.flags & CA_F_AT_GOAL) {
+        if (!(a.flags & CA_F_WAS_AT_GOAL)) r = p.r_goal;
+      } else if (!(a.flags & CA_F_WAS_IN_COLLISION)) {
+        if (coll) {
+          r = p.r_coll;
+          a.flags |= CA_F_IN_COLLISION;
+        } else if (nearest <= p.close_range) {
+          r = -0.1 - nearest / 2.;
+        }
+      }
+      r = fmin(fmax(r, p.r_min), p.r_max);
+      if (p.over_mode == CA_OVER_FIRST_AGENT_DONE && i > 0) r = 0.0;  // rewards = rewards[0] (:365-366)
+    } else {
+      r = 0.0;
+    }
+    // ---- _check_which_agents_done (:411-439)
+    const bool dn = valid ? (a.flags & CA_F_DONE_MASK) != 0 : true;
+    const bool learning = valid && (a.policy == CA_POLICY_LEARNING_GA3C || a.policy == CA_POLICY_LEARNING);
+    bool blocks_over;  // this agent keeps the episode alive
+    if (p.over_mode == CA_OVER_ALL_DONE) blocks_over = valid && !dn;
+    else if (p.over_mode == CA_OVER_FIRST_AGENT_DONE) blocks_over = valid && i == 0 && !dn;
+    else blocks_over = learning && !dn;
+    const unsigned alive = __ballot_sync(kFull, blocks_over) & gmask;
+    const bool over = alive == 0u;
+    if (world_ok) {
+      p.reward[g] = (float)r;
+      p.done[g] = dn ? 1 : 0;
+      if (i == 0) p.over[w] = over ? 1 : 0;
+    }
+    do_reset = world_ok && over && p.auto_reset;
+    write_obs_row(p, sm, a, e, world_ok, valid, n, i, base, tid, row, sidx_row);
+  } else {
+    do_reset = world_ok && (p.mask == nullptr || p.mask[w] != 0);
+  }
+
+  // ---- reset path (CollisionAvoidanceEnv.reset :196-215; DummyVecEnv auto-reset when called from step).
+  // Lanes whose world does not reset still take part in the shuffles but compute and write nothing.
+  if (!kStep || __any_sync(kFull, do_reset)) {
+    const bool again = kStep ? do_reset : true;  // this lane (re)computes its observation
+    if (do_reset) {
+      if (valid) load_agent(p.s0, g, a);
+      e = ego_frame(a.px, a.py, a.gx, a.gy, a.hd);
+    }
+    bool c_unused;
+    double n_unused;
+    pair_pass<false>(p, sm, a, e, valid && again, n, i, base, tid, c_unused, n_unused);
+    write_obs_row(p, sm, a, e, world_ok && again, valid && again, n, i, base, tid, row, sidx_row);
+  }
+
+  // ---- state write-back (coalesced; goal only changes for static agents / on reset)
+  if (valid) {
+    StateArrays s = p.s;
+    if (kStep || do_reset) {
+      s.px[g] = a.px; s.py[g] = a.py; s.hd[g] = a.hd; s.vx[g] = a.vx; s.vy[g] = a.vy; s.tr[g] = a.tr;
+      s.flags[g] = (uint8_t)a.flags;
+      if (do_reset || a.policy == CA_POLICY_STATIC) { s.gx[g] = a.gx; s.gy[g] = a.gy; }
+    }
+  }
+
+  store_tile(p, sm.tile, first_world_cta, tid);
+}
+
+// n-step discounted return, ProcessAgent._accumulate_rewards recursion (GA3C/ProcessAgent.py:71-76)
+__global__ void nstep_returns_kernel(const float* __restrict__ reward, const float* __restrict__ bootstrap,
+                                     float* __restrict__ out, int T, int N, float gamma) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= N) return;
+  float R = bootstrap[k];
+  for (int t = T - 1; t >= 0; --t) {
+    R = gamma * R + reward[(size_t)t * N + k];
+    out[(size_t)t * N + k] = R;
+  }
+}
+
+}  // namespace ca

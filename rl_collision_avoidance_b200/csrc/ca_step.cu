@@ -1,0 +1,451 @@
+// ca_step.cu — host side of libcastep.so: the C-ABI of include/ca_step.h over the kernels in ca_kernels.cuh.
+// No torch, no CPU fallback: every entry point needs a CUDA device.
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <string>
+
+#include "ca_kernels.cuh"
+
+namespace {
+
+thread_local std::string g_last_error;
+
+int fail(int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_last_error = buf;
+  return code;
+}
+
+#define CA_CUDA(expr)                                                                                      \
+  do {                                                                                                     \
+    cudaError_t _e = (expr);                                                                               \
+    if (_e != cudaSuccess)                                                                                 \
+      return fail(CA_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+  } while (0)
+
+// Makes env->device current for the duration of a call and restores the caller's device afterwards.
+struct DeviceGuard {
+  int prev = -1;
+  bool ok = true;
+  explicit DeviceGuard(int dev) {
+    if (cudaGetDevice(&prev) != cudaSuccess) { ok = false; return; }
+    if (prev != dev && cudaSetDevice(dev) != cudaSuccess) ok = false;
+    target = dev;
+  }
+  ~DeviceGuard() {
+    if (ok && prev >= 0 && prev != target) cudaSetDevice(prev);
+  }
+  int target = -1;
+};
+
+}  // namespace
+
+struct ca_env {
+  ca_config cfg;
+  int W = 0, A = 0, M = 0, L = 0, wpw = 0;
+  int grid = 0;
+  size_t smem_bytes = 0;
+  int tile_floats = 0;
+  bool bulk_ok = true;
+  double* slab = nullptr;      // 20 double arrays of W*A: live state then snapshot
+  uint8_t* bytes = nullptr;    // 4 uint8 arrays of W*A: flags, policy, flags0, policy0
+  int32_t* nag = nullptr;      // [W]
+  ca::StateArrays s{}, s0{};
+  bool initialised = false;
+  int64_t launches = 0;
+  // staging for the *_host entry points (lazily allocated)
+  cudaStream_t hstream = nullptr;
+  int32_t* d_actions = nullptr;
+  double* d_cont = nullptr;
+  float* d_obs = nullptr;
+  float* d_reward = nullptr;
+  uint8_t* d_done = nullptr;
+  uint8_t* d_over = nullptr;
+  uint8_t* d_mask = nullptr;
+  int32_t* d_sidx = nullptr;
+};
+
+namespace {
+
+using ca::kBlock;
+using ca::kWarps;
+
+// init[W][A][CA_INIT_STRIDE] (AoS, float64) -> SoA snapshot + live state.  Agent.__init__/reset, agent.py:29-136.
+__global__ void unpack_init_kernel(const double* __restrict__ init, const int32_t* __restrict__ nag_in,
+                                   int32_t* __restrict__ nag, ca::StateArrays s, ca::StateArrays s0, int W, int A,
+                                   double max_time_ratio, double thr, double dt) {
+  const long g = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= (long)W * A) return;
+  const int w = (int)(g / A), i = (int)(g - (long)w * A);
+  int n = nag_in[w];
+  n = n < 1 ? 1 : (n > A ? A : n);
+  if (i == 0) nag[w] = n;
+  double v[CA_INIT_STRIDE];
+#pragma unroll
+  for (int c = 0; c < CA_INIT_STRIDE; ++c) v[c] = i < n ? init[g * CA_INIT_STRIDE + c] : 0.0;
+  double t0 = v[CA_I_TIME_REMAINING];
+  if (i < n && isnan(t0)) {  // agent.py:98-103 (np.linalg.norm accumulates with FMA, see oracle np_norm2)
+    const double ex = v[CA_I_PX] - v[CA_I_GX], ey = v[CA_I_PY] - v[CA_I_GY];
+    const double nrm = sqrt(__fma_rn(ey, ey, __dmul_rn(ex, ex)));
+    t0 = max_time_ratio * ((nrm - thr) / v[CA_I_PREF_SPEED]);
+    if (!(t0 > dt)) t0 = dt;
+  }
+  s0.px[g] = s.px[g] = v[CA_I_PX];
+  s0.py[g] = s.py[g] = v[CA_I_PY];
+  s0.hd[g] = s.hd[g] = v[CA_I_HEADING];
+  s0.vx[g] = s.vx[g] = 0.0;
+  s0.vy[g] = s.vy[g] = 0.0;
+  s0.tr[g] = s.tr[g] = i < n ? t0 : 0.0;
+  s0.gx[g] = s.gx[g] = v[CA_I_GX];
+  s0.gy[g] = s.gy[g] = v[CA_I_GY];
+  s0.rad[g] = s.rad[g] = v[CA_I_RADIUS];
+  s0.ps[g] = s.ps[g] = v[CA_I_PREF_SPEED];
+  s0.flags[g] = s.flags[g] = 0;
+  s0.policy[g] = s.policy[g] = (uint8_t)(int)v[CA_I_POLICY];
+}
+
+__global__ void pack_state_kernel(ca::StateArrays s, double* __restrict__ out, long total) {
+  const long g = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= total) return;
+  double* r = out + g * CA_STATE_STRIDE;
+  r[CA_S_PX] = s.px[g]; r[CA_S_PY] = s.py[g]; r[CA_S_HEADING] = s.hd[g]; r[CA_S_VX] = s.vx[g]; r[CA_S_VY] = s.vy[g];
+  r[CA_S_TIME_REMAINING] = s.tr[g]; r[CA_S_GX] = s.gx[g]; r[CA_S_GY] = s.gy[g]; r[CA_S_RADIUS] = s.rad[g];
+  r[CA_S_PREF_SPEED] = s.ps[g]; r[CA_S_FLAGS] = (double)s.flags[g]; r[CA_S_POLICY] = (double)s.policy[g];
+}
+
+void carve(ca_env* e) {
+  const size_t n = (size_t)e->W * e->A;
+  double* d = e->slab;
+  ca::StateArrays* arr[2] = {&e->s, &e->s0};
+  for (int k = 0; k < 2; ++k) {
+    ca::StateArrays* s = arr[k];
+    s->px = d; d += n; s->py = d; d += n; s->hd = d; d += n; s->vx = d; d += n; s->vy = d; d += n;
+    s->tr = d; d += n; s->gx = d; d += n; s->gy = d; d += n; s->rad = d; d += n; s->ps = d; d += n;
+  }
+  e->s.flags = e->bytes; e->s.policy = e->bytes + n; e->s0.flags = e->bytes + 2 * n; e->s0.policy = e->bytes + 3 * n;
+}
+
+ca::Params make_params(const ca_env* e) {
+  ca::Params p;
+  memset(&p, 0, sizeof(p));
+  const ca_config& c = e->cfg;
+  p.W = e->W; p.A = e->A; p.M = e->M; p.L = e->L; p.wpw = e->wpw;
+  p.sort_method = c.sort_method; p.over_mode = c.game_over_mode; p.auto_reset = c.auto_reset;
+  p.tile_floats = e->tile_floats;
+  p.dt = c.dt;
+  p.thr_sq = std::pow(c.near_goal_threshold, 2.0);  // near_goal_threshold**2 as Python evaluates it (agent.py:150)
+  p.close_range = c.getting_close_range;
+  p.r_goal = c.reward_at_goal; p.r_coll = c.reward_collision_with_agent; p.r_step = c.reward_time_step;
+  p.r_min = c.min_possible_reward; p.r_max = c.max_possible_reward;
+  p.max_heading_change = c.max_heading_change;
+  p.sensing_horizon = c.sensing_horizon;
+  p.s = e->s; p.s0 = e->s0; p.nag = e->nag;
+  return p;
+}
+
+bool aligned16(const void* ptr) { return (reinterpret_cast<uintptr_t>(ptr) & 15u) == 0; }
+
+int launch_world_kernel(ca_env* e, bool step, ca::Params& p, cudaStream_t st) {
+  p.use_bulk_store = (e->bulk_ok && aligned16(p.obs) && (e->tile_floats % 4) == 0) ? 1 : 0;
+  if (step) ca::ca_world_kernel<true><<<e->grid, kBlock, e->smem_bytes, st>>>(p);
+  else ca::ca_world_kernel<false><<<e->grid, kBlock, e->smem_bytes, st>>>(p);
+  CA_CUDA(cudaPeekAtLastError());
+  e->launches += 1;
+  return CA_OK;
+}
+
+int ensure_staging(ca_env* e) {
+  if (e->hstream) return CA_OK;
+  const size_t n = (size_t)e->W * e->A;
+  CA_CUDA(cudaStreamCreateWithFlags(&e->hstream, cudaStreamNonBlocking));
+  CA_CUDA(cudaMalloc(&e->d_actions, n * sizeof(int32_t)));
+  CA_CUDA(cudaMalloc(&e->d_cont, n * 2 * sizeof(double)));
+  CA_CUDA(cudaMalloc(&e->d_obs, n * e->L * sizeof(float)));
+  CA_CUDA(cudaMalloc(&e->d_reward, n * sizeof(float)));
+  CA_CUDA(cudaMalloc(&e->d_done, n));
+  CA_CUDA(cudaMalloc(&e->d_over, (size_t)e->W));
+  CA_CUDA(cudaMalloc(&e->d_mask, (size_t)e->W));
+  CA_CUDA(cudaMalloc(&e->d_sidx, n * e->M * sizeof(int32_t)));
+  CA_CUDA(cudaMemsetAsync(e->d_actions, 0, n * sizeof(int32_t), e->hstream));
+  return CA_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int ca_abi_version(void) { return CA_ABI_VERSION; }
+
+const char* ca_last_error(void) { return g_last_error.c_str(); }
+
+const char* ca_strerror(int code) {
+  switch (code) {
+    case CA_OK: return "ok";
+    case CA_ERR_INVALID_ARG: return "invalid argument";
+    case CA_ERR_CUDA: return "CUDA error";
+    case CA_ERR_NOT_INITIALISED: return "world state not set (call ca_set_world_state first)";
+    case CA_ERR_UNSUPPORTED: return "unsupported configuration";
+    case CA_ERR_ALLOC: return "allocation failed";
+    default: return "unknown error";
+  }
+}
+
+int ca_default_config(ca_config* cfg, int32_t num_worlds, int32_t max_agents) {
+  if (!cfg) return fail(CA_ERR_INVALID_ARG, "cfg is NULL");
+  memset(cfg, 0, sizeof(*cfg));
+  cfg->abi_version = CA_ABI_VERSION;
+  cfg->num_worlds = num_worlds;
+  cfg->max_agents = max_agents;
+  cfg->max_others_observed = max_agents > 1 ? max_agents - 1 : 1;
+  cfg->sort_method = CA_SORT_CLOSEST_FIRST;
+  cfg->game_over_mode = CA_OVER_ALL_LEARNING_DONE;
+  cfg->auto_reset = 0;
+  cfg->device = 0;
+  cfg->dt = 0.2;                            // GCA/envs/config.py:45
+  cfg->near_goal_threshold = 0.2;           // :46
+  cfg->getting_close_range = 0.2;           // :39
+  cfg->reward_at_goal = 1.0;                // :30
+  cfg->reward_collision_with_agent = -0.25; // :31
+  cfg->reward_time_step = 0.0;              // :35
+  cfg->min_possible_reward = -0.25;         // collision_avoidance_env.py:475-483
+  cfg->max_possible_reward = 1.0;
+  cfg->max_time_ratio = 2.0;                // :47
+  cfg->max_heading_change = 3.141592653589793 / 3;  // collision_avoidance_env.py:76
+  cfg->sensing_horizon = INFINITY;          // :76
+  return CA_OK;
+}
+
+int ca_create(const ca_config* cfg, ca_env** out) {
+  if (!cfg || !out) return fail(CA_ERR_INVALID_ARG, "cfg/out is NULL");
+  *out = nullptr;
+  if (cfg->abi_version != CA_ABI_VERSION)
+    return fail(CA_ERR_INVALID_ARG, "abi_version %d != %d", cfg->abi_version, CA_ABI_VERSION);
+  if (cfg->num_worlds < 1) return fail(CA_ERR_INVALID_ARG, "num_worlds must be >= 1");
+  if (cfg->max_agents < 1 || cfg->max_agents > CA_MAX_AGENTS)
+    return fail(CA_ERR_INVALID_ARG, "max_agents must be in 1..%d", CA_MAX_AGENTS);
+  if (cfg->max_others_observed < 1 || cfg->max_others_observed > CA_MAX_AGENTS - 1)
+    return fail(CA_ERR_INVALID_ARG, "max_others_observed must be in 1..%d", CA_MAX_AGENTS - 1);
+  if (cfg->sort_method < 0 || cfg->sort_method > CA_SORT_TIME_TO_IMPACT)
+    return fail(CA_ERR_INVALID_ARG, "bad sort_method %d", cfg->sort_method);
+  if (cfg->game_over_mode < 0 || cfg->game_over_mode > CA_OVER_FIRST_AGENT_DONE)
+    return fail(CA_ERR_INVALID_ARG, "bad game_over_mode %d", cfg->game_over_mode);
+  if (!(cfg->dt > 0)) return fail(CA_ERR_INVALID_ARG, "dt must be > 0");
+  if ((int64_t)cfg->num_worlds * cfg->max_agents * CA_OBS_LEN(cfg->max_others_observed) > (int64_t)1 << 40)
+    return fail(CA_ERR_INVALID_ARG, "problem too large");
+  int ndev = 0;
+  CA_CUDA(cudaGetDeviceCount(&ndev));
+  if (cfg->device < 0 || cfg->device >= ndev)
+    return fail(CA_ERR_CUDA, "device %d not available (%d CUDA devices visible)", cfg->device, ndev);
+  DeviceGuard guard(cfg->device);
+  if (!guard.ok) return fail(CA_ERR_CUDA, "cudaSetDevice(%d) failed", cfg->device);
+
+  ca_env* e = new (std::nothrow) ca_env();
+  if (!e) return fail(CA_ERR_ALLOC, "out of host memory");
+  e->cfg = *cfg;
+  e->W = cfg->num_worlds; e->A = cfg->max_agents; e->M = cfg->max_others_observed;
+  e->L = CA_OBS_LEN(e->M);
+  e->wpw = 32 / e->A;
+  const int worlds_per_cta = kWarps * e->wpw;
+  e->grid = (e->W + worlds_per_cta - 1) / worlds_per_cta;
+  e->tile_floats = worlds_per_cta * e->A * e->L;
+  const size_t tile_bytes = (((size_t)e->tile_floats * 4 + 127) / 128) * 128;
+  const int nkeys = cfg->sort_method == CA_SORT_TIME_TO_IMPACT ? 4 : 3;
+  e->smem_bytes = tile_bytes + (size_t)nkeys * e->A * kBlock * sizeof(double);
+  const char* nb = getenv("CA_DISABLE_BULK_STORE");
+  e->bulk_ok = !(nb && nb[0] == '1');
+  int max_optin = 0;
+  cudaError_t ce = cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, cfg->device);
+  if (ce != cudaSuccess) { delete e; return fail(CA_ERR_CUDA, "cudaDeviceGetAttribute: %s", cudaGetErrorString(ce)); }
+  if (e->smem_bytes > (size_t)max_optin) {
+    delete e;
+    return fail(CA_ERR_UNSUPPORTED, "configuration needs %zu B shared memory per CTA, device allows %d", e->smem_bytes, max_optin);
+  }
+  ce = cudaFuncSetAttribute(ca::ca_world_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem_bytes);
+  if (ce == cudaSuccess)
+    ce = cudaFuncSetAttribute(ca::ca_world_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem_bytes);
+  if (ce != cudaSuccess) {
+    delete e;
+    return fail(CA_ERR_CUDA, "kernel image not usable on this device (built for sm_100a): %s", cudaGetErrorString(ce));
+  }
+  const size_t n = (size_t)e->W * e->A;
+  if (cudaMalloc(&e->slab, n * 20 * sizeof(double)) != cudaSuccess || cudaMalloc(&e->bytes, n * 4) != cudaSuccess ||
+      cudaMalloc(&e->nag, (size_t)e->W * sizeof(int32_t)) != cudaSuccess) {
+    cudaFree(e->slab); cudaFree(e->bytes); cudaFree(e->nag);
+    delete e;
+    cudaGetLastError();
+    return fail(CA_ERR_ALLOC, "cudaMalloc of %zu state bytes failed", n * 20 * sizeof(double));
+  }
+  carve(e);
+  *out = e;
+  return CA_OK;
+}
+
+int ca_destroy(ca_env* e) {
+  if (!e) return CA_OK;
+  DeviceGuard guard(e->cfg.device);
+  cudaDeviceSynchronize();
+  cudaFree(e->slab); cudaFree(e->bytes); cudaFree(e->nag);
+  cudaFree(e->d_actions); cudaFree(e->d_cont); cudaFree(e->d_obs); cudaFree(e->d_reward);
+  cudaFree(e->d_done); cudaFree(e->d_over); cudaFree(e->d_mask); cudaFree(e->d_sidx);
+  if (e->hstream) cudaStreamDestroy(e->hstream);
+  delete e;
+  return CA_OK;
+}
+
+int ca_set_world_state(ca_env* e, const double* init, const int32_t* num_agents, int on_device, void* stream) {
+  if (!e || !init || !num_agents) return fail(CA_ERR_INVALID_ARG, "NULL argument");
+  DeviceGuard guard(e->cfg.device);
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t n = (size_t)e->W * e->A;
+  const double* d_init = init;
+  const int32_t* d_nag = num_agents;
+  double* tmp_init = nullptr;
+  int32_t* tmp_nag = nullptr;
+  if (!on_device) {
+    for (int w = 0; w < e->W; ++w)
+      if (num_agents[w] < 1 || num_agents[w] > e->A)
+        return fail(CA_ERR_INVALID_ARG, "num_agents[%d] = %d outside 1..%d", w, num_agents[w], e->A);
+    CA_CUDA(cudaMalloc(&tmp_init, n * CA_INIT_STRIDE * sizeof(double)));
+    CA_CUDA(cudaMalloc(&tmp_nag, (size_t)e->W * sizeof(int32_t)));
+    CA_CUDA(cudaMemcpyAsync(tmp_init, init, n * CA_INIT_STRIDE * sizeof(double), cudaMemcpyHostToDevice, st));
+    CA_CUDA(cudaMemcpyAsync(tmp_nag, num_agents, (size_t)e->W * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    d_init = tmp_init;
+    d_nag = tmp_nag;
+  }
+  const int threads = 256;
+  const int blocks = (int)((n + threads - 1) / threads);
+  unpack_init_kernel<<<blocks, threads, 0, st>>>(d_init, d_nag, e->nag, e->s, e->s0, e->W, e->A, e->cfg.max_time_ratio,
+                                                 e->cfg.near_goal_threshold, e->cfg.dt);
+  CA_CUDA(cudaPeekAtLastError());
+  e->launches += 1;
+  if (!on_device) {
+    CA_CUDA(cudaStreamSynchronize(st));
+    cudaFree(tmp_init);
+    cudaFree(tmp_nag);
+  }
+  e->initialised = true;
+  return CA_OK;
+}
+
+int ca_reset(ca_env* e, const uint8_t* world_mask, float* obs, int32_t* sorted_idx, void* stream) {
+  if (!e || !obs) return fail(CA_ERR_INVALID_ARG, "NULL argument");
+  if (!e->initialised) return fail(CA_ERR_NOT_INITIALISED, "ca_reset before ca_set_world_state");
+  DeviceGuard guard(e->cfg.device);
+  ca::Params p = make_params(e);
+  p.mask = world_mask; p.obs = obs; p.sidx = sorted_idx;
+  return launch_world_kernel(e, false, p, (cudaStream_t)stream);
+}
+
+int ca_step(ca_env* e, const int32_t* actions, const double* cont_actions, float* obs, float* reward, uint8_t* done,
+            uint8_t* game_over, int32_t* sorted_idx, void* stream) {
+  if (!e || !actions || !obs || !reward || !done || !game_over) return fail(CA_ERR_INVALID_ARG, "NULL argument");
+  if (!e->initialised) return fail(CA_ERR_NOT_INITIALISED, "ca_step before ca_set_world_state");
+  DeviceGuard guard(e->cfg.device);
+  ca::Params p = make_params(e);
+  p.actions = actions; p.cont = cont_actions; p.obs = obs; p.reward = reward; p.done = done; p.over = game_over;
+  p.sidx = sorted_idx;
+  return launch_world_kernel(e, true, p, (cudaStream_t)stream);
+}
+
+int ca_step_host(ca_env* e, const int32_t* actions, const double* cont_actions, float* obs, float* reward,
+                 uint8_t* done, uint8_t* game_over, int32_t* sorted_idx) {
+  if (!e || !actions || !obs || !reward || !done || !game_over) return fail(CA_ERR_INVALID_ARG, "NULL argument");
+  if (!e->initialised) return fail(CA_ERR_NOT_INITIALISED, "ca_step_host before ca_set_world_state");
+  DeviceGuard guard(e->cfg.device);
+  int rc = ensure_staging(e);
+  if (rc != CA_OK) return rc;
+  const size_t n = (size_t)e->W * e->A;
+  cudaStream_t st = e->hstream;
+  CA_CUDA(cudaMemcpyAsync(e->d_actions, actions, n * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+  if (cont_actions) CA_CUDA(cudaMemcpyAsync(e->d_cont, cont_actions, n * 2 * sizeof(double), cudaMemcpyHostToDevice, st));
+  ca::Params p = make_params(e);
+  p.actions = e->d_actions; p.cont = cont_actions ? e->d_cont : nullptr; p.obs = e->d_obs; p.reward = e->d_reward;
+  p.done = e->d_done; p.over = e->d_over; p.sidx = sorted_idx ? e->d_sidx : nullptr;
+  rc = launch_world_kernel(e, true, p, st);
+  if (rc != CA_OK) return rc;
+  CA_CUDA(cudaMemcpyAsync(obs, e->d_obs, n * e->L * sizeof(float), cudaMemcpyDeviceToHost, st));
+  CA_CUDA(cudaMemcpyAsync(reward, e->d_reward, n * sizeof(float), cudaMemcpyDeviceToHost, st));
+  CA_CUDA(cudaMemcpyAsync(done, e->d_done, n, cudaMemcpyDeviceToHost, st));
+  CA_CUDA(cudaMemcpyAsync(game_over, e->d_over, (size_t)e->W, cudaMemcpyDeviceToHost, st));
+  if (sorted_idx) CA_CUDA(cudaMemcpyAsync(sorted_idx, e->d_sidx, n * e->M * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  CA_CUDA(cudaStreamSynchronize(st));
+  return CA_OK;
+}
+
+int ca_reset_host(ca_env* e, const uint8_t* world_mask, float* obs, int32_t* sorted_idx) {
+  if (!e || !obs) return fail(CA_ERR_INVALID_ARG, "NULL argument");
+  if (!e->initialised) return fail(CA_ERR_NOT_INITIALISED, "ca_reset_host before ca_set_world_state");
+  DeviceGuard guard(e->cfg.device);
+  int rc = ensure_staging(e);
+  if (rc != CA_OK) return rc;
+  const size_t n = (size_t)e->W * e->A;
+  cudaStream_t st = e->hstream;
+  if (world_mask) CA_CUDA(cudaMemcpyAsync(e->d_mask, world_mask, (size_t)e->W, cudaMemcpyHostToDevice, st));
+  ca::Params p = make_params(e);
+  p.mask = world_mask ? e->d_mask : nullptr; p.obs = e->d_obs; p.sidx = sorted_idx ? e->d_sidx : nullptr;
+  rc = launch_world_kernel(e, false, p, st);
+  if (rc != CA_OK) return rc;
+  CA_CUDA(cudaMemcpyAsync(obs, e->d_obs, n * e->L * sizeof(float), cudaMemcpyDeviceToHost, st));
+  if (sorted_idx) CA_CUDA(cudaMemcpyAsync(sorted_idx, e->d_sidx, n * e->M * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  CA_CUDA(cudaStreamSynchronize(st));
+  return CA_OK;
+}
+
+int ca_get_state(ca_env* e, double* out, int on_device, void* stream) {
+  if (!e || !out) return fail(CA_ERR_INVALID_ARG, "NULL argument");
+  if (!e->initialised) return fail(CA_ERR_NOT_INITIALISED, "ca_get_state before ca_set_world_state");
+  DeviceGuard guard(e->cfg.device);
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t n = (size_t)e->W * e->A;
+  double* d_out = out;
+  if (!on_device) CA_CUDA(cudaMalloc(&d_out, n * CA_STATE_STRIDE * sizeof(double)));
+  const int threads = 256;
+  pack_state_kernel<<<(int)((n + threads - 1) / threads), threads, 0, st>>>(e->s, d_out, (long)n);
+  CA_CUDA(cudaPeekAtLastError());
+  e->launches += 1;
+  if (!on_device) {
+    CA_CUDA(cudaMemcpyAsync(out, d_out, n * CA_STATE_STRIDE * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CA_CUDA(cudaStreamSynchronize(st));
+    cudaFree(d_out);
+  }
+  return CA_OK;
+}
+
+int ca_launch_count(const ca_env* e, int64_t* out) {
+  if (!e || !out) return fail(CA_ERR_INVALID_ARG, "NULL argument");
+  *out = e->launches;
+  return CA_OK;
+}
+
+int ca_host_alloc(void** out, uint64_t bytes) {
+  if (!out) return fail(CA_ERR_INVALID_ARG, "NULL argument");
+  CA_CUDA(cudaHostAlloc(out, (size_t)bytes, cudaHostAllocDefault));
+  return CA_OK;
+}
+
+int ca_host_free(void* ptr) {
+  if (ptr) CA_CUDA(cudaFreeHost(ptr));
+  return CA_OK;
+}
+
+int ca_nstep_returns(const float* reward, const float* bootstrap, float* out, int32_t T, int32_t N, float gamma,
+                     int device, void* stream) {
+  if (!reward || !bootstrap || !out || T < 0 || N < 1) return fail(CA_ERR_INVALID_ARG, "bad argument");
+  DeviceGuard guard(device);
+  if (!guard.ok) return fail(CA_ERR_CUDA, "cudaSetDevice(%d) failed", device);
+  const int threads = 256;
+  ca::nstep_returns_kernel<<<(N + threads - 1) / threads, threads, 0, (cudaStream_t)stream>>>(reward, bootstrap, out, T,
+                                                                                              N, gamma);
+  CA_CUDA(cudaPeekAtLastError());
+  return CA_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,390 @@
+"""GPU parity tests proper: the CUDA path (through the C-ABI of include/ca_step.h) against
+  (1) golden vectors recorded from the unmodified reference, and
+  (2) the CPU oracle on seeded random inputs,
+bit-exact for flags / done / game_over / neighbour indices, and within the stated float tolerances:
+  float64 state (pos, heading, vel, time remaining): 1e-9 abs
+  float32 observations and rewards: 1e-5 abs (BASELINE.json north_star tolerance).
+At BASELINE's full sizes the oracle is too slow to run every step, so size-independent properties are
+checked instead (world independence, determinism, padding rows, flag state-machine invariants).
+"""
+import numpy as np
+import pytest
+
+from rl_collision_avoidance_b200 import _abi
+from tests.golden_util import GOLDEN_KINDS, Golden, replay_and_compare
+
+pytestmark = pytest.mark.gpu
+
+STATE_TOL = 1e-9
+OBS_TOL = 1e-5
+REWARD_TOL = 1e-5
+
+
+def _host_env(cfg):
+    from rl_collision_avoidance_b200.vec_env import HostVecEnv
+    return HostVecEnv(cfg, want_sorted_idx=True)
+
+
+class _DeviceEnvAdapter(object):
+    """numpy façade over the device-pointer path (ca_step with torch tensors)."""
+
+    def __init__(self, cfg):
+        import torch
+        from rl_collision_avoidance_b200.vec_env import VecCollisionAvoidanceEnv
+        self.torch = torch
+        self.env = VecCollisionAvoidanceEnv(cfg, want_sorted_idx=True)
+
+    def set_world_state(self, init, nag):
+        self.env.set_world_state(init, nag)
+
+    def _pull(self):
+        e = self.env
+        self.obs = e.obs.cpu().numpy()
+        self.reward = e.reward.cpu().numpy()
+        self.done = e.done.cpu().numpy()
+        self.game_over = e.game_over.cpu().numpy()
+        self.sorted_idx = e.sorted_idx.cpu().numpy()
+
+    def reset(self, mask=None):
+        self.env.reset(mask)
+        self._pull()
+        return self.obs
+
+    def step(self, actions, cont=None):
+        t = self.torch
+        a = t.from_numpy(np.ascontiguousarray(actions, dtype=np.int32)).cuda()
+        c = None if cont is None else t.from_numpy(np.ascontiguousarray(cont, dtype=np.float64)).cuda()
+        self.env.step(a, c)
+        self._pull()
+        return self.obs, self.reward, self.done, self.game_over
+
+    def get_state(self):
+        return self.env.get_state()
+
+    def close(self):
+        self.env.close()
+
+
+# ----------------------------------------------------------------------------- golden vectors (reference)
+
+@pytest.mark.parametrize("kind", GOLDEN_KINDS)
+def test_cuda_matches_reference_golden_host_api(kind):
+    gold = Golden(kind)
+    names = gold.cases("B")
+    env = _host_env(gold.config(len(names)))
+    checked = replay_and_compare(gold, names, env, state_tol=STATE_TOL, obs_tol=OBS_TOL, reward_tol=REWARD_TOL)
+    assert checked > 50
+    env.close()
+
+
+@pytest.mark.parametrize("kind", ["phase1", "phase2", "clip_last"])
+def test_cuda_matches_reference_golden_device_api(kind):
+    gold = Golden(kind)
+    names = gold.cases("B")
+    env = _DeviceEnvAdapter(gold.config(len(names)))
+    replay_and_compare(gold, names, env, state_tol=STATE_TOL, obs_tol=OBS_TOL, reward_tol=REWARD_TOL)
+    env.close()
+
+
+def test_cuda_config1_two_agents_100_random_actions():
+    """BASELINE config #1: single 2-agent world, 100 random actions, fixed seed (here on the GPU)."""
+    gold = Golden("phase1")
+    env = _host_env(gold.config(1))
+    n = replay_and_compare(gold, ["config1_modeB"], env, state_tol=STATE_TOL, obs_tol=OBS_TOL, reward_tol=REWARD_TOL)
+    assert n == int(gold.get("config1_modeB", "steps"))
+    env.close()
+
+
+# ----------------------------------------------------------------------------- oracle on seeded inputs
+
+def _random_worlds(rng, W, A, side, policies=(0,), ragged=True):
+    px = rng.uniform(-side, side, (W, A)); py = rng.uniform(-side, side, (W, A))
+    gx = rng.uniform(-side, side, (W, A)); gy = rng.uniform(-side, side, (W, A))
+    # keep start-goal >= 2 m like the reference generator (gen_rand_testcases.py:218)
+    close = np.hypot(gx - px, gy - py) < 2.0
+    gx = np.where(close, px + 2.5, gx)
+    from rl_collision_avoidance_b200.vec_env import make_init
+    init = make_init(px, py, gx, gy, rng.uniform(0.5, 2.0, (W, A)), rng.uniform(0.2, 0.8, (W, A)),
+                     rng.uniform(-np.pi, np.pi, (W, A)), rng.choice(list(policies), size=(W, A)))
+    nag = rng.integers(min(2, A), A + 1, W).astype(np.int32) if ragged else np.full(W, A, np.int32)
+    return init, nag
+
+
+def _compare_step(gpu, cpu, tag):
+    np.testing.assert_array_equal(gpu.done, cpu.done, err_msg=tag + " done")
+    np.testing.assert_array_equal(gpu.game_over, cpu.game_over, err_msg=tag + " game_over")
+    np.testing.assert_array_equal(gpu.sorted_idx, cpu.sorted_idx, err_msg=tag + " sorted idx")
+    np.testing.assert_allclose(gpu.obs, cpu.obs, rtol=0, atol=OBS_TOL, err_msg=tag + " obs")
+    np.testing.assert_allclose(gpu.reward, cpu.reward, rtol=0, atol=REWARD_TOL, err_msg=tag + " reward")
+
+
+def _compare_state(gpu, cpu, tag):
+    gs, cs = gpu.get_state(), cpu.get_state()
+    np.testing.assert_array_equal(gs[..., _abi.S_FLAGS], cs[..., _abi.S_FLAGS], err_msg=tag + " flags")
+    np.testing.assert_array_equal(gs[..., _abi.S_POLICY], cs[..., _abi.S_POLICY], err_msg=tag + " policy")
+    np.testing.assert_allclose(gs, cs, rtol=0, atol=STATE_TOL, err_msg=tag + " state")
+
+
+@pytest.mark.parametrize("A,M,W,side,sort", [
+    (2, 1, 300, 3.0, "closest_first"),
+    (3, 2, 301, 3.0, "closest_last"),
+    (4, 3, 1027, 3.5, "closest_first"),
+    (4, 3, 515, 3.5, "time_to_impact"),
+    (5, 4, 257, 4.0, "closest_first"),
+    (7, 3, 259, 4.0, "closest_last"),       # clipping: up to 6 others, 3 observed
+    (10, 9, 263, 5.0, "closest_first"),
+    (10, 9, 131, 5.0, "closest_last"),
+    (16, 15, 67, 6.0, "closest_first"),
+    (20, 6, 33, 7.0, "time_to_impact"),     # clipping with TTI
+    (32, 31, 19, 9.0, "closest_first"),
+    (1, 1, 40, 3.0, "closest_first"),
+])
+def test_cuda_matches_oracle_random_worlds(A, M, W, side, sort):
+    from oracle.ca_oracle import OracleEnv
+    rng = np.random.default_rng(1000 + 7 * A + M)
+    init, nag = _random_worlds(rng, W, A, side, policies=(0, 0, 0, 1, 2), ragged=True)
+    cfg = _abi.default_config(W, A, M, sort_method=_abi.SORT_METHODS[sort])
+    gpu, cpu = _host_env(cfg), OracleEnv(cfg)
+    gpu.set_world_state(init, nag); cpu.set_world_state(init, nag)
+    gpu.reset(); cpu.reset()
+    np.testing.assert_allclose(gpu.obs, cpu.obs, rtol=0, atol=OBS_TOL)
+    np.testing.assert_array_equal(gpu.sorted_idx, cpu.sorted_idx)
+    for t in range(70):
+        # biased towards driving forward so goals, collisions and time-outs all occur
+        act = rng.choice([0, 1, 2, 2, 2, 3, 4, 5, 6, 7, 8, 9, 10], size=(W, A)).astype(np.int32)
+        gpu.step(act); cpu.step(act)
+        _compare_step(gpu, cpu, "A=%d t=%d" % (A, t))
+        if t % 10 == 9:
+            _compare_state(gpu, cpu, "A=%d t=%d" % (A, t))
+    # every flag kind must have occurred, otherwise the test is too easy
+    fl = cpu.get_state()[..., _abi.S_FLAGS].astype(int)
+    if A >= 3:
+        for bit in (_abi.F_AT_GOAL, _abi.F_IN_COLLISION, _abi.F_RAN_OUT_OF_TIME):
+            assert np.any(fl & bit), "flag %d never set" % bit
+    gpu.close(); cpu.close()
+
+
+def test_cuda_continuous_learning_policy_matches_oracle():
+    from oracle.ca_oracle import OracleEnv
+    rng = np.random.default_rng(5)
+    W, A = 200, 4
+    init, nag = _random_worlds(rng, W, A, 3.5, policies=(3, 3, 1, 0), ragged=True)
+    cfg = _abi.default_config(W, A)
+    gpu, cpu = _host_env(cfg), OracleEnv(cfg)
+    gpu.set_world_state(init, nag); cpu.set_world_state(init, nag)
+    gpu.reset(); cpu.reset()
+    for t in range(40):
+        act = rng.integers(0, 11, (W, A)).astype(np.int32)
+        cont = np.stack([rng.uniform(0, 1, (W, A)), rng.uniform(0, 1, (W, A))], axis=-1)
+        gpu.step(act, cont); cpu.step(act, cont)
+        _compare_step(gpu, cpu, "cont t=%d" % t)
+    # NULL cont_actions = no-op command for CA_POLICY_LEARNING agents
+    gpu.step(act, None); cpu.step(act, None)
+    _compare_step(gpu, cpu, "cont none")
+    _compare_state(gpu, cpu, "cont")
+    gpu.close(); cpu.close()
+
+
+@pytest.mark.parametrize("mode", [_abi.OVER_ALL_LEARNING_DONE, _abi.OVER_ALL_DONE, _abi.OVER_FIRST_AGENT_DONE])
+def test_cuda_auto_reset_matches_oracle(mode):
+    """DummyVecEnv semantics: a finished world reloads its initial state in the same launch; obs is the new
+    episode's first observation while reward/done/game_over describe the finished step."""
+    from oracle.ca_oracle import OracleEnv
+    rng = np.random.default_rng(77)
+    W, A = 333, 4
+    init, nag = _random_worlds(rng, W, A, 3.0, policies=(0, 0, 1, 2), ragged=True)
+    cfg = _abi.default_config(W, A, auto_reset=1, game_over_mode=mode)
+    gpu, cpu = _host_env(cfg), OracleEnv(cfg)
+    gpu.set_world_state(init, nag); cpu.set_world_state(init, nag)
+    gpu.reset(); cpu.reset()
+    overs = 0
+    for t in range(150):
+        act = rng.choice([1, 2, 2, 2, 3, 6, 9], size=(W, A)).astype(np.int32)
+        gpu.step(act); cpu.step(act)
+        _compare_step(gpu, cpu, "auto_reset t=%d" % t)
+        overs += int(cpu.game_over.sum())
+        if t % 25 == 24:
+            _compare_state(gpu, cpu, "auto_reset t=%d" % t)
+    assert overs > W  # most worlds finished at least once and kept running
+    gpu.close(); cpu.close()
+
+
+def test_cuda_masked_reset_matches_oracle():
+    from oracle.ca_oracle import OracleEnv
+    rng = np.random.default_rng(78)
+    W, A = 130, 4
+    init, nag = _random_worlds(rng, W, A, 3.0)
+    cfg = _abi.default_config(W, A)
+    gpu, cpu = _host_env(cfg), OracleEnv(cfg)
+    gpu.set_world_state(init, nag); cpu.set_world_state(init, nag)
+    gpu.reset(); cpu.reset()
+    for t in range(30):
+        act = rng.integers(0, 11, (W, A)).astype(np.int32)
+        gpu.step(act); cpu.step(act)
+        if t % 7 == 6:
+            mask = (rng.random(W) < 0.3).astype(np.uint8)
+            gpu.reset(mask); cpu.reset(mask)
+            np.testing.assert_allclose(gpu.obs, cpu.obs, rtol=0, atol=OBS_TOL)
+            np.testing.assert_array_equal(gpu.sorted_idx, cpu.sorted_idx)
+            _compare_state(gpu, cpu, "masked reset t=%d" % t)
+    gpu.close(); cpu.close()
+
+
+def test_library_computes_time_remaining_when_nan():
+    from oracle.ca_oracle import OracleEnv
+    rng = np.random.default_rng(79)
+    W, A = 64, 4
+    init, nag = _random_worlds(rng, W, A, 3.0)
+    assert np.all(np.isnan(init[..., _abi.I_TIME_REMAINING]))
+    cfg = _abi.default_config(W, A)
+    gpu, cpu = _host_env(cfg), OracleEnv(cfg)
+    gpu.set_world_state(init, nag); cpu.set_world_state(init, nag)
+    gs, cs = gpu.get_state(), cpu.get_state()
+    np.testing.assert_array_equal(gs[..., _abi.S_TIME_REMAINING], cs[..., _abi.S_TIME_REMAINING])
+    d = np.hypot(init[..., 0] - init[..., 2], init[..., 1] - init[..., 3])
+    expect = np.maximum(2.0 * (d - 0.2) / init[..., _abi.I_PREF_SPEED], 0.2)
+    live = np.arange(A)[None, :] < nag[:, None]
+    np.testing.assert_allclose(gs[..., _abi.S_TIME_REMAINING][live], expect[live], rtol=1e-12)
+    gpu.close(); cpu.close()
+
+
+def test_bulk_store_and_plain_store_paths_agree(monkeypatch):
+    """The TMA bulk-store tile path and the scalar-store fallback write identical observations."""
+    rng = np.random.default_rng(80)
+    W, A = 640, 4
+    init, nag = _random_worlds(rng, W, A, 3.0)
+    acts = rng.integers(0, 11, (20, W, A)).astype(np.int32)
+    outs = []
+    for disable in ("0", "1"):
+        monkeypatch.setenv("CA_DISABLE_BULK_STORE", disable)
+        env = _host_env(_abi.default_config(W, A))
+        env.set_world_state(init, nag)
+        env.reset()
+        o = [env.obs.copy()]
+        for t in range(20):
+            env.step(acts[t])
+            o.append(env.obs.copy())
+        outs.append(np.stack(o))
+        env.close()
+    np.testing.assert_array_equal(outs[0], outs[1])
+
+
+# ----------------------------------------------------------------------------- full-size properties
+
+def _full_size_inputs(W, A, seed):
+    rng = np.random.default_rng(seed)
+    side = 3.5 if A <= 4 else 5.0
+    return _random_worlds(rng, W, A, side, policies=(0, 0, 0, 0, 1, 2), ragged=True) + (rng,)
+
+
+@pytest.mark.parametrize("W,A", [(65536, 4), (16384, 10)])
+def test_full_size_world_independence_and_invariants(W, A):
+    """BASELINE configs #2/#3 sizes: a slice of worlds stepped inside the big batch is bit-identical to the same
+    worlds stepped alone (and the alone run is oracle-checked), the run is deterministic, and the flag state
+    machine invariants hold everywhere."""
+    from oracle.ca_oracle import OracleEnv
+    init, nag, rng = _full_size_inputs(W, A, 2024)
+    T = 24
+    acts = rng.choice([0, 1, 2, 2, 2, 3, 4, 6, 9], size=(T, W, A)).astype(np.int32)
+    sl = slice(W // 2 - 100, W // 2 + 157)   # 257 worlds straddling CTA boundaries
+    Ws = sl.stop - sl.start
+    big = _host_env(_abi.default_config(W, A))
+    small = _host_env(_abi.default_config(Ws, A))
+    cpu = OracleEnv(_abi.default_config(Ws, A))
+    big.set_world_state(init, nag); small.set_world_state(init[sl], nag[sl]); cpu.set_world_state(init[sl], nag[sl])
+    big.reset(); small.reset(); cpu.reset()
+    np.testing.assert_array_equal(big.obs[sl], small.obs)
+    live = np.arange(A)[None, :] < nag[:, None]
+    prev_done = np.zeros((W, A), dtype=np.uint8)
+    first_obs_sum = None
+    for t in range(T):
+        big.step(acts[t]); small.step(acts[t][sl]); cpu.step(acts[t][sl])
+        # slice inside the big batch == alone (bit-identical), alone == oracle (tolerance)
+        np.testing.assert_array_equal(big.obs[sl], small.obs)
+        np.testing.assert_array_equal(big.reward[sl], small.reward)
+        np.testing.assert_array_equal(big.done[sl], small.done)
+        np.testing.assert_array_equal(big.game_over[sl], small.game_over)
+        np.testing.assert_array_equal(big.sorted_idx[sl], small.sorted_idx)
+        _compare_step(small, cpu, "full-size slice t=%d" % t)
+        # invariants over the whole batch
+        assert np.all(big.done[~live] == 1) and np.all(big.reward[~live] == 0)
+        assert np.all(big.obs[~live] == 0), "rows of absent agents must be zero"
+        assert np.all(big.done >= prev_done), "done is monotone without reset"
+        prev_done = big.done.copy()
+        assert np.all(np.isfinite(big.obs))
+        assert np.all((big.reward >= -0.25) & (big.reward <= 1.0))
+        num_others = big.obs[..., 1]
+        assert np.all(num_others[live] == np.minimum(nag[:, None] - 1, A - 1).repeat(A, 1)[live])
+        learning = big.obs[..., 0] == 1
+        expect_over = np.all(~learning | (big.done == 1), axis=1)
+        np.testing.assert_array_equal(big.game_over, expect_over.astype(np.uint8))
+        # heading_ego within [-pi, pi), distances non-negative
+        assert np.all(big.obs[..., 3] >= -np.pi - 1e-6) and np.all(big.obs[..., 3] <= np.pi + 1e-6)
+        assert np.all(big.obs[..., 2] >= 0)
+        if t == 0:
+            first_obs_sum = float(big.obs.astype(np.float64).sum())
+    st_big = big.get_state()
+    np.testing.assert_array_equal(st_big[sl], small.get_state())
+    # determinism: a second run from the same inputs reproduces the same bits
+    again = _host_env(_abi.default_config(W, A))
+    again.set_world_state(init, nag); again.reset()
+    for t in range(T):
+        again.step(acts[t])
+        if t == 0:
+            assert float(again.obs.astype(np.float64).sum()) == first_obs_sum
+    np.testing.assert_array_equal(again.get_state(), st_big)
+    np.testing.assert_array_equal(again.obs, big.obs)
+    for e in (big, small, again):
+        e.close()
+    cpu.close()
+
+
+def test_world_permutation_equivariance():
+    """Permuting worlds permutes outputs (no cross-world coupling through shuffles or the shared-memory tile)."""
+    rng = np.random.default_rng(31)
+    W, A = 4099, 4
+    init, nag = _random_worlds(rng, W, A, 3.5, policies=(0, 0, 1, 2))
+    perm = rng.permutation(W)
+    a, b = _host_env(_abi.default_config(W, A)), _host_env(_abi.default_config(W, A))
+    a.set_world_state(init, nag); b.set_world_state(init[perm], nag[perm])
+    a.reset(); b.reset()
+    for t in range(30):
+        act = rng.integers(0, 11, (W, A)).astype(np.int32)
+        a.step(act); b.step(act[perm])
+        np.testing.assert_array_equal(a.obs[perm], b.obs)
+        np.testing.assert_array_equal(a.reward[perm], b.reward)
+        np.testing.assert_array_equal(a.done[perm], b.done)
+        np.testing.assert_array_equal(a.game_over[perm], b.game_over)
+    a.close(); b.close()
+
+
+# ----------------------------------------------------------------------------- error behaviour
+
+def test_errors_are_loud():
+    from rl_collision_avoidance_b200._lib import CaError
+    env = _host_env(_abi.default_config(8, 4))
+    with pytest.raises(CaError):
+        env.step(np.zeros((8, 4), dtype=np.int32))          # before ca_set_world_state
+    with pytest.raises(ValueError):
+        env.set_world_state(np.zeros((8, 3, _abi.INIT_STRIDE)), np.full(8, 2))
+    with pytest.raises(ValueError):
+        init = np.zeros((8, 4, _abi.INIT_STRIDE))
+        env.set_world_state(init, np.full(8, 5))             # more agents than A
+    env.close()
+
+
+def test_nstep_returns_kernel_matches_oracle():
+    import ctypes as C
+    import torch
+    from oracle import ca_oracle
+    from rl_collision_avoidance_b200._lib import check, lib
+    rng = np.random.default_rng(3)
+    T, N, gamma = 20, 5000, 0.97
+    r = rng.normal(size=(T, N)).astype(np.float32)
+    b = rng.normal(size=(N,)).astype(np.float32)
+    dr, db = torch.from_numpy(r).cuda(), torch.from_numpy(b).cuda()
+    out = torch.empty_like(dr)
+    check(lib().ca_nstep_returns(C.c_void_p(dr.data_ptr()), C.c_void_p(db.data_ptr()), C.c_void_p(out.data_ptr()),
+                                 T, N, gamma, 0, C.c_void_p(torch.cuda.current_stream().cuda_stream)), "ca_nstep_returns")
+    ref = ca_oracle.nstep_returns(r, b, gamma)
+    np.testing.assert_allclose(out.cpu().numpy(), ref, rtol=0, atol=1e-4)
