@@ -76,6 +76,24 @@ class Golden(object):
         return init, nag, T
 
 
+def obs_abs_diff(a, b):
+    """|a - b| per observation element, with column 3 (heading_ego_frame, an angle in [-pi, pi)) compared on the
+    circle: -pi and +pi are the same heading.  The reference itself lands on either side of that seam depending
+    on the last ulp of atan2 (e.g. a non-cooperative agent that overshoots its goal faces exactly away from it),
+    so a 2*pi jump there is a representation artefact, not a discrepancy."""
+    d = np.abs(np.asarray(a, dtype=np.float64) - np.asarray(b, dtype=np.float64))
+    d[..., 3] = np.minimum(d[..., 3], np.abs(2 * np.pi - d[..., 3]))
+    return d
+
+
+def assert_obs_close(a, b, atol, err_msg=""):
+    d = obs_abs_diff(a, b)
+    if not np.all(d <= atol):
+        idx = np.unravel_index(np.argmax(d), d.shape)
+        raise AssertionError("%s: max obs abs diff %.3e at %s (tol %.1e): %r vs %r" % (
+            err_msg, d[idx], idx, atol, np.asarray(a)[idx], np.asarray(b)[idx]))
+
+
 GOLDEN_FLAG_BITS = (_abi.F_AT_GOAL, _abi.F_WAS_AT_GOAL, _abi.F_IN_COLLISION, _abi.F_WAS_IN_COLLISION,
                     _abi.F_RAN_OUT_OF_TIME)
 
@@ -91,7 +109,7 @@ def replay_and_compare(gold, names, env, state_tol, obs_tol, reward_tol, check_s
     obs = np.asarray(env.obs, dtype=np.float64)
     for w, name in enumerate(names):
         n = nag[w]
-        np.testing.assert_allclose(obs[w], gold.get(name, "obs0"), rtol=0, atol=obs_tol, err_msg="%s obs0" % name)
+        assert_obs_close(obs[w], gold.get(name, "obs0"), obs_tol, "%s obs0" % name)
         np.testing.assert_array_equal(np.asarray(env.sorted_idx)[w, :n], gold.get(name, "sorted0"), err_msg="%s sorted0" % name)
     checked = 0
     for t in range(T):
@@ -127,7 +145,7 @@ def replay_and_compare(gold, names, env, state_tol, obs_tol, reward_tol, check_s
             assert np.all(sidx[w, n:] == -1), tag
             np.testing.assert_allclose(rew[w, :n], gold.get(name, "reward")[t], rtol=0, atol=reward_tol, err_msg=tag + " reward")
             assert np.all(rew[w, n:] == 0), tag
-            np.testing.assert_allclose(obs[w], gold.get(name, "obs")[t], rtol=0, atol=obs_tol, err_msg=tag + " obs")
+            assert_obs_close(obs[w], gold.get(name, "obs")[t], obs_tol, tag + " obs")
             if st is not None:
                 s = st[w, :n]
                 fl = s[:, _abi.S_FLAGS].astype(np.int64)

@@ -11,7 +11,7 @@ import numpy as np
 import pytest
 
 from rl_collision_avoidance_b200 import _abi
-from tests.golden_util import GOLDEN_KINDS, Golden, replay_and_compare
+from tests.golden_util import GOLDEN_KINDS, Golden, assert_obs_close, replay_and_compare
 
 pytestmark = pytest.mark.gpu
 
@@ -114,7 +114,7 @@ def _compare_step(gpu, cpu, tag):
     np.testing.assert_array_equal(gpu.done, cpu.done, err_msg=tag + " done")
     np.testing.assert_array_equal(gpu.game_over, cpu.game_over, err_msg=tag + " game_over")
     np.testing.assert_array_equal(gpu.sorted_idx, cpu.sorted_idx, err_msg=tag + " sorted idx")
-    np.testing.assert_allclose(gpu.obs, cpu.obs, rtol=0, atol=OBS_TOL, err_msg=tag + " obs")
+    assert_obs_close(gpu.obs, cpu.obs, OBS_TOL, tag + " obs")
     np.testing.assert_allclose(gpu.reward, cpu.reward, rtol=0, atol=REWARD_TOL, err_msg=tag + " reward")
 
 
@@ -147,7 +147,7 @@ def test_cuda_matches_oracle_random_worlds(A, M, W, side, sort):
     gpu, cpu = _host_env(cfg), OracleEnv(cfg)
     gpu.set_world_state(init, nag); cpu.set_world_state(init, nag)
     gpu.reset(); cpu.reset()
-    np.testing.assert_allclose(gpu.obs, cpu.obs, rtol=0, atol=OBS_TOL)
+    assert_obs_close(gpu.obs, cpu.obs, OBS_TOL, "reset obs")
     np.testing.assert_array_equal(gpu.sorted_idx, cpu.sorted_idx)
     for t in range(70):
         # biased towards driving forward so goals, collisions and time-outs all occur
@@ -224,7 +224,7 @@ def test_cuda_masked_reset_matches_oracle():
         if t % 7 == 6:
             mask = (rng.random(W) < 0.3).astype(np.uint8)
             gpu.reset(mask); cpu.reset(mask)
-            np.testing.assert_allclose(gpu.obs, cpu.obs, rtol=0, atol=OBS_TOL)
+            assert_obs_close(gpu.obs, cpu.obs, OBS_TOL, "masked reset obs")
             np.testing.assert_array_equal(gpu.sorted_idx, cpu.sorted_idx)
             _compare_state(gpu, cpu, "masked reset t=%d" % t)
     gpu.close(); cpu.close()
