@@ -321,7 +321,7 @@ def run_ours(args):
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": ncu_traffic_per_launch(), "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": ALG_BYTES_PER_AGENT_STEP * W * A,
-                         "kernel": "ca::ca_world_kernel<true>", "launch_ms": launch_ms},
+                         "kernel": "ca::ca_step_kernel<4>", "launch_ms": launch_ms},
         }
         if world_size == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline_run(args.cpu_seconds, 16384)

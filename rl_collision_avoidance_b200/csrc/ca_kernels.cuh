@@ -38,6 +38,7 @@ struct Params {
   int sort_method, over_mode, auto_reset;
   int tile_floats;      // floats in the CTA's obs tile = kWarps * wpw * A * L
   int use_bulk_store;   // 1: TMA bulk store of full tiles
+  int warp_store;       // specialised kernel: each warp stores its own rows (warp tile is a multiple of 16 B)
   double dt, thr_sq, close_range, r_goal, r_coll, r_step, r_min, r_max, max_heading_change, sensing_horizon;
   StateArrays s;        // live state
   StateArrays s0;       // snapshot injected by ca_set_world_state (for reset)

@@ -9,6 +9,7 @@
 #include <string>
 
 #include "ca_kernels.cuh"
+#include "ca_step_fast.cuh"
 
 namespace {
 
@@ -55,6 +56,8 @@ struct ca_env {
   size_t smem_bytes = 0;
   int tile_floats = 0;
   bool bulk_ok = true;
+  bool force_generic = false;
+  size_t smem_fast = 0;        // dynamic shared memory of the specialised step kernel (observation tile only)
   double* slab = nullptr;      // 20 double arrays of W*A: live state then snapshot
   uint8_t* bytes = nullptr;    // 4 uint8 arrays of W*A: flags, policy, flags0, policy0
   int32_t* nag = nullptr;      // [W]
@@ -153,10 +156,43 @@ ca::Params make_params(const ca_env* e) {
 
 bool aligned16(const void* ptr) { return (reinterpret_cast<uintptr_t>(ptr) & 15u) == 0; }
 
+// The specialised step kernels (ca_step_fast.cuh) exist for these agent-slot counts.
+#define CA_FAST_SIZES(X) X(2) X(3) X(4) X(5) X(6) X(8) X(10)
+
+bool has_fast_kernel(const ca_env* e) {
+  if (e->force_generic || e->cfg.sort_method == CA_SORT_TIME_TO_IMPACT) return false;
+  switch (e->A) {
+#define X(n) case n:
+    CA_FAST_SIZES(X)
+#undef X
+    return true;
+    default: return false;
+  }
+}
+
+cudaError_t set_fast_smem_attr(int A, int bytes) {
+  switch (A) {
+#define X(n) case n: return cudaFuncSetAttribute(ca::ca_step_kernel<n>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    CA_FAST_SIZES(X)
+#undef X
+    default: return cudaSuccess;
+  }
+}
+
 int launch_world_kernel(ca_env* e, bool step, ca::Params& p, cudaStream_t st) {
   p.use_bulk_store = (e->bulk_ok && aligned16(p.obs) && (e->tile_floats % 4) == 0) ? 1 : 0;
-  if (step) ca::ca_world_kernel<true><<<e->grid, kBlock, e->smem_bytes, st>>>(p);
-  else ca::ca_world_kernel<false><<<e->grid, kBlock, e->smem_bytes, st>>>(p);
+  p.warp_store = ((e->tile_floats / kWarps) % 4) == 0 ? 1 : 0;
+  if (step && has_fast_kernel(e)) {
+    switch (e->A) {
+#define X(n) case n: ca::ca_step_kernel<n><<<e->grid, kBlock, e->smem_fast, st>>>(p); break;
+      CA_FAST_SIZES(X)
+#undef X
+    }
+  } else if (step) {
+    ca::ca_world_kernel<true><<<e->grid, kBlock, e->smem_bytes, st>>>(p);
+  } else {
+    ca::ca_world_kernel<false><<<e->grid, kBlock, e->smem_bytes, st>>>(p);
+  }
   CA_CUDA(cudaPeekAtLastError());
   e->launches += 1;
   return CA_OK;
@@ -259,8 +295,11 @@ int ca_create(const ca_config* cfg, ca_env** out) {
   const size_t tile_bytes = (((size_t)e->tile_floats * 4 + 127) / 128) * 128;
   const int nkeys = cfg->sort_method == CA_SORT_TIME_TO_IMPACT ? 4 : 3;
   e->smem_bytes = tile_bytes + (size_t)nkeys * e->A * kBlock * sizeof(double);
+  e->smem_fast = tile_bytes;
   const char* nb = getenv("CA_DISABLE_BULK_STORE");
   e->bulk_ok = !(nb && nb[0] == '1');
+  const char* fg = getenv("CA_FORCE_GENERIC");
+  e->force_generic = fg && fg[0] == '1';
   int max_optin = 0;
   cudaError_t ce = cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, cfg->device);
   if (ce != cudaSuccess) { delete e; return fail(CA_ERR_CUDA, "cudaDeviceGetAttribute: %s", cudaGetErrorString(ce)); }
@@ -271,6 +310,7 @@ int ca_create(const ca_config* cfg, ca_env** out) {
   ce = cudaFuncSetAttribute(ca::ca_world_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem_bytes);
   if (ce == cudaSuccess)
     ce = cudaFuncSetAttribute(ca::ca_world_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem_bytes);
+  if (ce == cudaSuccess) ce = set_fast_smem_attr(e->A, (int)e->smem_fast);
   if (ce != cudaSuccess) {
     delete e;
     return fail(CA_ERR_CUDA, "kernel image not usable on this device (built for sm_100a): %s", cudaGetErrorString(ce));

@@ -1,0 +1,305 @@
+// ca_step_fast.cuh — the step kernel specialised on the number of agent slots per world (kA).
+//
+// Same algorithm, data layout and numerics as ca_world_kernel<true> (ca_kernels.cuh), but with kA a
+// compile-time constant every per-other loop is fully unrolled: the lane's sort keys, relative positions
+// and centre distances of its (kA-1) potential neighbours live in registers, the neighbour order is a
+// pairwise rank (each unordered pair of keys is compared once) and nothing but the finished observation
+// rows goes through shared memory.  Used for closest_first / closest_last sorting; time_to_impact sorting,
+// reset, and agent counts without an instantiation run on the generic kernel.
+#pragma once
+#include "ca_kernels.cuh"
+
+namespace ca {
+
+template <int kA>
+struct Others {
+  static constexpr int kN = kA > 1 ? kA - 1 : 1;
+  double key[kN];   // signed rint(100 * dist_2_other); +inf for an absent / unobserved other
+  double po[kN];    // p_orth
+  double d[kN];     // centre distance
+  double rx[kN], ry[kN], rr[kN];  // relative position and radius of the other
+};
+
+// Sensor first loop (OtherAgentsStatesSensor.sense :72-103) + _check_for_collisions (:370-409) for the lane's
+// agent against its k-th other, j = k + (k >= i).  All lanes of the warp execute the shuffles.
+template <int kA, bool kCollide>
+__device__ __forceinline__ void fast_pair_pass(const Params& p, const Agent& a, const Ego& e, bool valid, int n, int i,
+                                               int base, Others<kA>& o, bool& coll, double& nearest) {
+  coll = false;
+  nearest = INFINITY;
+  const bool horizon = isfinite(p.sensing_horizon);
+#pragma unroll
+  for (int k = 0; k < kA - 1; ++k) {
+    const int j = k + (k >= i ? 1 : 0);
+    const int src = (base + j) & 31;
+    const double xj = shfl_d(a.px, src), yj = shfl_d(a.py, src), rj = shfl_d(a.rad, src);
+    const bool live = valid && j < n;
+    const double rx = xj - a.px, ry = yj - a.py;
+    const double d = sqrt(rx * rx + ry * ry);  // l2norm / vec2_l2_norm (util.py:8-12,106-112)
+    if (kCollide && live) {
+      const double R = a.rad + rj;
+      if (d <= R) coll = true;
+      if (j > i) nearest = fmin(nearest, d - R);  // only the lower index is updated (:393)
+    }
+    const bool seen = live && !(horizon && d > p.sensing_horizon);
+    o.key[k] = seen ? rint((d - a.rad - rj) * 100.0) : INFINITY;
+    o.po[k] = dot2(rx, ry, -e.pry, e.prx);
+    o.d[k] = d;
+    o.rx[k] = rx; o.ry[k] = ry; o.rr[k] = rj;
+  }
+}
+
+// (key, p_orth, list position) strict order; k1 < k2 so a full tie keeps k1 first (stable sort).
+__device__ __forceinline__ bool first_before_second(double q1, double p1, double q2, double p2) {
+  return (q1 < q2) || (q1 == q2 && p1 <= p2);
+}
+
+template <int kA>
+__device__ __forceinline__ void fast_write_obs_row(const Params& p, const Agent& a, const Ego& e, bool world_ok,
+                                                   bool valid, int i, int base, const Others<kA>& o, float* row,
+                                                   int32_t* sidx_row) {
+  constexpr int kN = kA - 1;
+  const int M = p.M;
+  int count = 0;
+#pragma unroll
+  for (int k = 0; k < kN; ++k) count += (o.key[k] < INFINITY) ? 1 : 0;
+  double key[kN > 0 ? kN : 1];
+#pragma unroll
+  for (int k = 0; k < kN; ++k) key[k] = o.key[k];
+  if (count > M) {
+    // first sort by (round(dist), p_orth) and keep the M closest (get_clipped_sorted_inds :31-38)
+    int rank1[kN > 0 ? kN : 1];
+#pragma unroll
+    for (int k = 0; k < kN; ++k) rank1[k] = 0;
+#pragma unroll
+    for (int k1 = 0; k1 < kN; ++k1)
+#pragma unroll
+      for (int k2 = k1 + 1; k2 < kN; ++k2) {
+        const bool b = first_before_second(o.key[k1], o.po[k1], o.key[k2], o.po[k2]);
+        rank1[k1] += b ? 0 : 1;
+        rank1[k2] += b ? 1 : 0;
+      }
+#pragma unroll
+    for (int k = 0; k < kN; ++k)
+      if (rank1[k] >= M) key[k] = INFINITY;
+    count = M;
+  }
+  if (p.sort_method == CA_SORT_CLOSEST_LAST) {  // final order by (-round(dist), p_orth) (:41-43)
+#pragma unroll
+    for (int k = 0; k < kN; ++k)
+      if (key[k] < INFINITY) key[k] = -key[k];
+  }
+  int slot[kN > 0 ? kN : 1];
+#pragma unroll
+  for (int k = 0; k < kN; ++k) slot[k] = 0;
+#pragma unroll
+  for (int k1 = 0; k1 < kN; ++k1)
+#pragma unroll
+    for (int k2 = k1 + 1; k2 < kN; ++k2) {
+      const bool b = first_before_second(key[k1], o.po[k1], key[k2], o.po[k2]);
+      slot[k1] += b ? 0 : 1;
+      slot[k2] += b ? 1 : 0;
+    }
+
+  if (world_ok) {
+    if (valid) {
+      row[0] = (a.policy == CA_POLICY_LEARNING_GA3C || a.policy == CA_POLICY_LEARNING) ? 1.f : 0.f;
+      row[1] = (float)count;
+      row[2] = (float)e.dist;
+      row[3] = (float)e.hego;
+      row[4] = (float)a.ps;
+      row[5] = (float)a.rad;
+      for (int q = CA_OBS_HOST_LEN + CA_OBS_OTHER_LEN * count; q < p.L; ++q) row[q] = 0.f;
+      if (sidx_row) for (int k = count; k < M; ++k) sidx_row[k] = -1;
+    } else {
+      for (int q = 0; q < p.L; ++q) row[q] = 0.f;
+      if (sidx_row) for (int k = 0; k < M; ++k) sidx_row[k] = -1;
+    }
+  }
+  // second loop of the sensor (:105-144): every lane takes part in the velocity shuffles
+#pragma unroll
+  for (int k = 0; k < kN; ++k) {
+    const int j = k + (k >= i ? 1 : 0);
+    const int src = (base + j) & 31;
+    const double vxj = shfl_d(a.vx, src), vyj = shfl_d(a.vy, src);
+    if (valid && key[k] < INFINITY) {
+      float* s = row + CA_OBS_HOST_LEN + CA_OBS_OTHER_LEN * slot[k];
+      s[0] = (float)dot2(o.rx[k], o.ry[k], e.prx, e.pry);
+      s[1] = (float)o.po[k];
+      s[2] = (float)dot2(vxj, vyj, e.prx, e.pry);
+      s[3] = (float)dot2(vxj, vyj, -e.pry, e.prx);
+      s[4] = (float)o.rr[k];
+      s[5] = (float)(a.rad + o.rr[k]);
+      s[6] = (float)(o.d[k] - a.rad - o.rr[k]);
+      if (sidx_row) sidx_row[slot[k]] = j;
+    }
+  }
+}
+
+// Warp-level store of the warp's observation rows (its wpw worlds are contiguous in global memory).
+template <int kA>
+__device__ __forceinline__ void fast_store_warp_tile(const Params& p, const float* wtile, long first_world_warp,
+                                                     int lane) {
+  constexpr int wpw = 32 / kA;
+  const long worlds_left = (long)p.W - first_world_warp;
+  if (worlds_left <= 0) return;
+  const int nw = worlds_left < wpw ? (int)worlds_left : wpw;
+  const int nfloats = nw * kA * p.L;
+  float* dst = p.obs + (size_t)first_world_warp * kA * p.L;
+  if (p.use_bulk_store && nw == wpw) {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncwarp();
+    if (lane == 0) {
+      asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(wtile)),
+                   "r"(nfloats * 4)
+                   : "memory");
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    }
+    return;
+  }
+  __syncwarp();
+  for (int q = lane; q < nfloats; q += 32) dst[q] = wtile[q];
+}
+
+template <int kA>
+__global__ void __launch_bounds__(kBlock) ca_step_kernel(const __grid_constant__ Params p) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  constexpr int wpw = 32 / kA;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int wl = lane / kA;
+  const int i = lane - wl * kA;
+  const int base = wl * kA;
+  const long first_world_warp = ((long)blockIdx.x * kWarps + warp) * wpw;
+  const long w = first_world_warp + wl;
+  const bool world_ok = wl < wpw && w < p.W;
+  const int n = world_ok ? p.nag[w] : 0;
+  const bool valid = world_ok && i < n;
+  const size_t g = world_ok ? (size_t)w * kA + i : 0;
+  const unsigned gmask = (kA >= 32 ? kFull : ((1u << kA) - 1u)) << (base & 31);
+
+  // per-warp tile: rows of the warp's wpw worlds; warp tiles are laid out back to back (no padding) so the
+  // CTA tile is also contiguous
+  float* wtile = reinterpret_cast<float*>(smem_raw) + (size_t)warp * wpw * kA * p.L;
+  float* row = wtile + ((size_t)wl * kA + i) * p.L;
+  int32_t* sidx_row = (p.sidx && world_ok) ? p.sidx + g * p.M : nullptr;
+
+  Agent a;
+  if (valid) load_agent(p.s, g, a); else zero_agent(a);
+  int act = 0;
+  if (valid) act = p.actions[g];
+
+  // ---- _take_action (:217-252)
+  const bool was_done = (a.flags & CA_F_DONE_MASK) != 0;
+  float cmd_speed = 0.f, cmd_dh = 0.f;
+  if (valid && !was_done) {
+    if (a.policy == CA_POLICY_NONCOOP) {
+      const Ego e0 = ego_frame(a.px, a.py, a.gx, a.gy, a.hd);
+      cmd_speed = (float)a.ps;
+      cmd_dh = (float)(-e0.hego);
+    } else if (a.policy == CA_POLICY_LEARNING_GA3C) {
+      const int k = act < 0 ? 0 : (act > 10 ? 10 : act);
+      cmd_speed = (float)(a.ps * kActSpeed[k]);
+      cmd_dh = (float)kActDhead[k];
+    } else if (a.policy == CA_POLICY_LEARNING) {
+      double e0 = 0.0, e1 = 0.5;
+      if (p.cont) { e0 = p.cont[2 * g]; e1 = p.cont[2 * g + 1]; }
+      cmd_speed = (float)(a.ps * e0);
+      cmd_dh = (float)(p.max_heading_change * (2. * e1 - 1.));
+    } else if (a.policy == CA_POLICY_STATIC) {
+      a.gx = a.px;
+      a.gy = a.py;
+    }
+  }
+  // ---- Agent.take_action (agent.py:190-238)
+  if (valid) {
+    if (was_done) {
+      if (a.flags & CA_F_AT_GOAL) a.flags |= CA_F_WAS_AT_GOAL;
+      if (a.flags & CA_F_IN_COLLISION) a.flags |= CA_F_WAS_IN_COLLISION;
+      a.vx = 0.0;
+      a.vy = 0.0;
+    } else {
+      const double speed = (double)cmd_speed;
+      const double h = wrap_angle((double)cmd_dh + a.hd);
+      double sh, ch;
+      sincos(h, &sh, &ch);
+      a.px += speed * ch * p.dt;
+      a.py += speed * sh * p.dt;
+      a.vx = speed * ch;
+      a.vy = speed * sh;
+      a.hd = h;
+      const double ex = a.px - a.gx, ey = a.py - a.gy;
+      if (ex * ex + ey * ey <= p.thr_sq) a.flags |= CA_F_AT_GOAL; else a.flags &= ~CA_F_AT_GOAL;
+      a.tr -= p.dt;
+      if (a.tr <= 0.0) a.flags |= CA_F_RAN_OUT_OF_TIME;
+    }
+  }
+
+  Ego e = ego_frame(a.px, a.py, a.gx, a.gy, a.hd);
+  Others<kA> o;
+  bool coll;
+  double nearest;
+  fast_pair_pass<kA, true>(p, a, e, valid, n, i, base, o, coll, nearest);
+
+  // ---- _compute_rewards (:319-368)
+  double r = p.r_step;
+  if (valid) {
+    if (a.flags & CA_F_AT_GOAL) {
+      if (!(a.flags & CA_F_WAS_AT_GOAL)) r = p.r_goal;
+    } else if (!(a.flags & CA_F_WAS_IN_COLLISION)) {
+      if (coll) {
+        r = p.r_coll;
+        a.flags |= CA_F_IN_COLLISION;
+      } else if (nearest <= p.close_range) {
+        r = -0.1 - nearest / 2.;
+      }
+    }
+    r = fmin(fmax(r, p.r_min), p.r_max);
+    if (p.over_mode == CA_OVER_FIRST_AGENT_DONE && i > 0) r = 0.0;
+  } else {
+    r = 0.0;
+  }
+  // ---- _check_which_agents_done (:411-439)
+  const bool dn = valid ? (a.flags & CA_F_DONE_MASK) != 0 : true;
+  const bool learning = valid && (a.policy == CA_POLICY_LEARNING_GA3C || a.policy == CA_POLICY_LEARNING);
+  bool blocks_over;
+  if (p.over_mode == CA_OVER_ALL_DONE) blocks_over = valid && !dn;
+  else if (p.over_mode == CA_OVER_FIRST_AGENT_DONE) blocks_over = valid && i == 0 && !dn;
+  else blocks_over = learning && !dn;
+  const unsigned alive = __ballot_sync(kFull, blocks_over) & gmask;
+  const bool over = alive == 0u;
+  if (world_ok) {
+    p.reward[g] = (float)r;
+    p.done[g] = dn ? 1 : 0;
+    if (i == 0) p.over[w] = over ? 1 : 0;
+  }
+  const bool do_reset = world_ok && over && p.auto_reset;
+
+  if (!__any_sync(kFull, do_reset)) {
+    fast_write_obs_row<kA>(p, a, e, world_ok, valid, i, base, o, row, sidx_row);
+  } else {
+    // DummyVecEnv semantics: worlds that finished reload their injected initial state and observe again;
+    // the other worlds of the warp observe their post-step state.
+    if (do_reset) {
+      if (valid) load_agent(p.s0, g, a);
+      e = ego_frame(a.px, a.py, a.gx, a.gy, a.hd);
+    }
+    bool c_unused;
+    double n_unused;
+    fast_pair_pass<kA, false>(p, a, e, valid, n, i, base, o, c_unused, n_unused);
+    fast_write_obs_row<kA>(p, a, e, world_ok, valid, i, base, o, row, sidx_row);
+  }
+
+  // ---- state write-back
+  if (valid) {
+    StateArrays s = p.s;
+    s.px[g] = a.px; s.py[g] = a.py; s.hd[g] = a.hd; s.vx[g] = a.vx; s.vy[g] = a.vy; s.tr[g] = a.tr;
+    s.flags[g] = (uint8_t)a.flags;
+    if (do_reset || a.policy == CA_POLICY_STATIC) { s.gx[g] = a.gx; s.gy[g] = a.gy; }
+  }
+
+  if (p.warp_store) fast_store_warp_tile<kA>(p, wtile, first_world_warp, lane);
+  else store_tile(p, reinterpret_cast<float*>(smem_raw), (long)blockIdx.x * kWarps * wpw, tid);
+}
+
+}  // namespace ca

@@ -269,6 +269,33 @@ def test_bulk_store_and_plain_store_paths_agree(monkeypatch):
     np.testing.assert_array_equal(outs[0], outs[1])
 
 
+@pytest.mark.parametrize("A,M,sort", [(2, 1, "closest_first"), (3, 2, "closest_last"), (4, 3, "closest_first"),
+                                      (5, 2, "closest_last"), (6, 5, "closest_first"), (8, 3, "closest_first"),
+                                      (10, 9, "closest_last")])
+def test_specialised_and_generic_kernels_agree_bitwise(monkeypatch, A, M, sort):
+    """ca_step_kernel<A> (unrolled, register keys) and the generic ca_world_kernel<true> are the same arithmetic."""
+    rng = np.random.default_rng(90 + A)
+    W = 777
+    init, nag = _random_worlds(rng, W, A, 3.0 + 0.3 * A, policies=(0, 0, 0, 1, 2))
+    acts = rng.choice([0, 1, 2, 2, 2, 3, 4, 6, 9], size=(40, W, A)).astype(np.int32)
+    outs = []
+    for force in ("0", "1"):
+        monkeypatch.setenv("CA_FORCE_GENERIC", force)
+        env = _host_env(_abi.default_config(W, A, M, sort_method=_abi.SORT_METHODS[sort], auto_reset=1))
+        env.set_world_state(init, nag)
+        env.reset()
+        rec = []
+        for t in range(40):
+            env.step(acts[t])
+            rec.append((env.obs.copy(), env.reward.copy(), env.done.copy(), env.game_over.copy(), env.sorted_idx.copy()))
+        outs.append((rec, env.get_state()))
+        env.close()
+    for t in range(40):
+        for x, y in zip(outs[0][0][t], outs[1][0][t]):
+            np.testing.assert_array_equal(x, y)
+    np.testing.assert_array_equal(outs[0][1], outs[1][1])
+
+
 # ----------------------------------------------------------------------------- full-size properties
 
 def _full_size_inputs(W, A, seed):
