@@ -22,6 +22,8 @@
  *                              and, with auto_reset, DummyVecEnv.step_wait (openai/baselines@ea25b9e, not vendored)
  *   ca_get_state               reading Agent attributes                 GCA/envs/agent.py:66-136
  *   ca_nstep_returns           ProcessAgent._accumulate_rewards         GA3C/ProcessAgent.py:54-79
+ *   ca_ga3c_record             ProcessAgent.run_episode bookkeeping     GA3C/ProcessAgent.py:105-211
+ *   ca_ga3c_episode_stats      ProcessAgent.run / ProcessStats.run      GA3C/ProcessAgent.py:220-243, ProcessStats.py:62-117
  *
  * Conventions
  *   - every function returns 0 (CA_OK) or a negative ca_status; nothing throws across the ABI;
@@ -191,6 +193,37 @@ int ca_host_free(void* ptr);
  *   out[t] = reward[t] + gamma * out[t+1], out[T] := bootstrap. */
 int ca_nstep_returns(const float* reward, const float* bootstrap, float* out, int32_t T, int32_t N,
                      float gamma, int device, void* stream);
+
+/* ---- GA3C actor bookkeeping (vectorised ProcessAgent.run_episode, GA3C/ProcessAgent.py:105-211) ----
+ * All pointers are device pointers owned by the caller.  N = W*A agent slots, R ring slots (R >= time_max + 2),
+ * L = observation length.  Ring slot of env step t is (t mod R); the env must have written the observation that
+ * step t's prediction was made from into obs_ring[t mod R] (pass obs_ring + ((t+1) mod R)*N*L as ca_step's obs). */
+typedef struct ca_ga3c_buffers {
+  const float* obs_ring;  /* [R][N][L] */
+  int32_t* act_ring;      /* [R][N] */
+  float* rew_ring;        /* [R][N]  rewards, overwritten in place by discounted returns like the reference */
+  int32_t* length;        /* [N] len(experiences[i]) */
+  int32_t* tcount;        /* [N] time_counts[i] */
+  uint8_t* done_trained;  /* [N] which_agents_done_and_trained[i] */
+  float* out_x;           /* [capacity][L-1] emitted x_ rows (observation without the is_learning column) */
+  float* out_r;           /* [capacity] emitted r_ (discounted returns) */
+  int32_t* out_a;         /* [capacity] emitted action indices (the reference one-hot encodes them) */
+  int32_t* out_count;     /* [1] rows emitted so far (caller zeroes it); > capacity means rows were dropped */
+  int32_t capacity;
+  int32_t reserved;
+} ca_ga3c_buffers;
+
+/* Append step t's experience of every learning agent and emit the training rows the reference's
+ * run_episode()/_accumulate_rewards() would yield at this step. */
+int ca_ga3c_record(const ca_ga3c_buffers* bufs, int64_t t, int32_t ring_slots, int32_t num_slots, int32_t agents_per_world,
+                   int32_t obs_len, int32_t time_max, float gamma, const int32_t* actions, const float* values,
+                   const float* reward, const uint8_t* done, const uint8_t* game_over, int device, void* stream);
+
+/* Episode statistics (ProcessAgent.run :220-243): obs_now = obs_ring slot of step t, ep_reward float[W] and
+ * ep_steps int32[W] are running accumulators, stats double[3] += {episodes, sum of scores, learning-agent steps}. */
+int ca_ga3c_episode_stats(const float* obs_now, const float* reward, const uint8_t* game_over, float* ep_reward,
+                          int32_t* ep_steps, double* stats, int32_t num_worlds, int32_t agents_per_world,
+                          int32_t obs_len, int device, void* stream);
 
 const char* ca_strerror(int code);
 const char* ca_last_error(void);

@@ -67,6 +67,14 @@ class CaConfig(C.Structure):
     ]
 
 
+class CaGa3cBuffers(C.Structure):
+    _fields_ = [
+        ("obs_ring", C.c_void_p), ("act_ring", C.c_void_p), ("rew_ring", C.c_void_p), ("length", C.c_void_p),
+        ("tcount", C.c_void_p), ("done_trained", C.c_void_p), ("out_x", C.c_void_p), ("out_r", C.c_void_p),
+        ("out_a", C.c_void_p), ("out_count", C.c_void_p), ("capacity", C.c_int32), ("reserved", C.c_int32),
+    ]
+
+
 def default_config(num_worlds, max_agents, max_others_observed=None, **overrides):
     """Reference defaults, GCA/envs/config.py:30-47,64-76,171 and collision_avoidance_env.py:76,463-483."""
     cfg = CaConfig()

@@ -1,0 +1,148 @@
+// ca_ga3c.cuh — device-side experience bookkeeping of the GA3C actor (vectorised ProcessAgent.run_episode).
+//
+// Reference: GA3C/ProcessAgent.py:105-211 (run_episode) and :54-79 (_accumulate_rewards).  There, every
+// learning agent of one env keeps a Python list of Experience objects that grows by one per env step and is
+// flushed to the trainer when the agent is done or after TIME_MAX steps (SURVEY.md §8 N10 lists the quirks:
+// the last experience is held back as the bootstrap unless the agent is done, a done agent keeps re-flushing
+// 2-element lists every step until the world ends, a terminal flush of exactly TIME_MAX+1 experiences emits the
+// terminal one separately with its raw reward, rewards are overwritten in place by the discounted return).
+//
+// Here the "list" of agent slot g is the window of the last `length[g]` time steps of three rings indexed by
+// (t mod R): the observation ring the env kernel writes into, an action ring and a (mutable) reward ring.
+// One thread per agent slot applies the list logic; emitted training rows (x = pre-step observation without
+// the is_learning column, discounted return, action index) are appended to compact output arrays, the slot
+// range being claimed with one atomicAdd per warp and the 26/68-float rows copied by the whole warp.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/ca_step.h"
+
+namespace ca {
+
+struct Ga3cParams {
+  ca_ga3c_buffers b;
+  long long t;     // global env-step counter; ring slot = t mod R
+  int R, N, A, L, time_max;
+  float gamma;
+  const int32_t* actions;  // [N] action taken at step t
+  const float* values;     // [N] V(s_t) predicted at step t
+  const float* reward;     // [N] reward of step t
+  const uint8_t* done;     // [N] which_agents_done after step t
+  const uint8_t* over;     // [N / A] game_over after step t
+};
+
+__global__ void __launch_bounds__(128) ga3c_record_kernel(const __grid_constant__ Ga3cParams p) {
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  const int R = p.R, L = p.L, XL = p.L - 1;
+  const size_t N = (size_t)p.N;
+  const int slot_now = (int)(p.t % R);
+  const bool in_range = g < p.N;
+  // is_learning is column 0 of the observation the prediction was made from (ProcessAgent.py:128-133)
+  const bool learning = in_range && p.b.obs_ring[((size_t)slot_now * N + g) * L] != 0.f;
+
+  int n_emit = 0;       // rows this agent emits: list elements [0, n_main) plus optionally the held-back last one
+  int n_main = 0, first_t_off = 0;
+  bool emit_last = false;
+  if (learning) {
+    const bool dn = p.done[g] != 0;
+    p.b.act_ring[(size_t)slot_now * N + g] = p.actions[g];
+    p.b.rew_ring[(size_t)slot_now * N + g] = p.reward[g];
+    int len = p.b.length[g] + 1;
+    int tc = p.b.tcount[g];
+    bool trained = p.b.done_trained[g] != 0;
+    if (dn || (tc == p.time_max && !trained)) {  // ProcessAgent.py:186 (operator precedence as written there)
+      float Rv = dn ? 0.f : p.values[g];
+      if (dn) trained = true;
+      first_t_off = len - 1;  // list element k lives at time t - first_t_off + k
+      if (len == 1) {
+        n_main = 1;           // returned unchanged, raw reward (:62-63)
+      } else {
+        emit_last = dn && len == p.time_max + 1;             // leftover_term_exp (:65-66)
+        n_main = (dn && len != p.time_max + 1) ? len : len - 1;
+        for (int k = n_main - 1; k >= 0; --k) {              // :71-76, rewards overwritten in place
+          const int s = (int)((p.t - first_t_off + k) % R);
+          float* r = &p.b.rew_ring[(size_t)s * N + g];
+          Rv = p.gamma * Rv + *r;
+          *r = Rv;
+        }
+      }
+      n_emit = n_main + (emit_last ? 1 : 0);
+      tc = 0;
+      len = 1;  // experiences[i] = [experiences[i][-1]] (:208)
+    }
+    tc += 1;
+    if (p.over[g / p.A]) { len = 0; tc = 0; trained = false; }  // the next run_episode() starts from scratch
+    p.b.length[g] = len;
+    p.b.tcount[g] = tc;
+    p.b.done_trained[g] = trained ? 1 : 0;
+  }
+
+  // claim output rows: exclusive prefix sum inside the warp, one atomicAdd per warp
+  int incl = n_emit;
+#pragma unroll
+  for (int off = 1; off < 32; off <<= 1) {
+    const int v = __shfl_up_sync(0xffffffffu, incl, off);
+    if (lane >= off) incl += v;
+  }
+  const int warp_total = __shfl_sync(0xffffffffu, incl, 31);
+  if (warp_total == 0) return;
+  int warp_base = 0;
+  if (lane == 31) warp_base = atomicAdd(p.b.out_count, warp_total);
+  warp_base = __shfl_sync(0xffffffffu, warp_base, 31);
+  const int my_base = warp_base + incl - n_emit;
+
+  // warp-cooperative row copy: for each lane with rows, all 32 lanes copy one row at a time (coalesced)
+  for (int src = 0; src < 32; ++src) {
+    const int cnt = __shfl_sync(0xffffffffu, n_emit, src);
+    if (cnt == 0) continue;
+    const int base = __shfl_sync(0xffffffffu, my_base, src);
+    const int g_src = __shfl_sync(0xffffffffu, g, src);
+    const int off = __shfl_sync(0xffffffffu, first_t_off, src);
+    const int nm = __shfl_sync(0xffffffffu, n_main, src);
+    for (int e = 0; e < cnt; ++e) {
+      const int row = base + e;
+      if (row >= p.b.capacity) break;  // overflow is reported through out_count > capacity
+      const int k = e < nm ? e : off;  // the optional extra row is the last list element
+      const int s = (int)((p.t - off + k) % R);
+      const float* x = p.b.obs_ring + ((size_t)s * N + g_src) * L + 1;  // drop the is_learning column
+      float* dst = p.b.out_x + (size_t)row * XL;
+      for (int q = lane; q < XL; q += 32) dst[q] = x[q];
+      if (lane == 0) {
+        p.b.out_r[row] = p.b.rew_ring[(size_t)s * N + g_src];
+        p.b.out_a[row] = p.b.act_ring[(size_t)s * N + g_src];
+      }
+    }
+  }
+}
+
+// Per-world episode statistics (ProcessAgent.run :220-243, ProcessStats.run :62-117): score = sum over learning
+// agents of their rewards / number of learning agents; length = frames pushed to the trainer.
+// stats[0] += finished episodes, stats[1] += sum of scores, stats[2] += learning-agent steps of finished episodes.
+__global__ void ga3c_episode_stats_kernel(const float* __restrict__ obs_now, const float* __restrict__ reward,
+                                          const uint8_t* __restrict__ over, float* __restrict__ ep_reward,
+                                          int32_t* __restrict__ ep_steps, double* __restrict__ stats, int W, int A,
+                                          int L) {
+  const int w = blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= W) return;
+  float sum = 0.f;
+  int learners = 0;
+  for (int i = 0; i < A; ++i) {
+    const size_t g = (size_t)w * A + i;
+    if (obs_now[g * L] != 0.f) { sum += reward[g]; ++learners; }
+  }
+  float acc = ep_reward[w] + sum;
+  int steps = ep_steps[w] + learners;
+  if (over[w]) {
+    atomicAdd(&stats[0], 1.0);
+    atomicAdd(&stats[1], learners > 0 ? (double)acc / learners : 0.0);
+    atomicAdd(&stats[2], (double)steps);
+    acc = 0.f;
+    steps = 0;
+  }
+  ep_reward[w] = acc;
+  ep_steps[w] = steps;
+}
+
+}  // namespace ca

@@ -10,6 +10,7 @@
 
 #include "ca_kernels.cuh"
 #include "ca_step_fast.cuh"
+#include "ca_ga3c.cuh"
 
 namespace {
 
@@ -484,6 +485,41 @@ int ca_nstep_returns(const float* reward, const float* bootstrap, float* out, in
   const int threads = 256;
   ca::nstep_returns_kernel<<<(N + threads - 1) / threads, threads, 0, (cudaStream_t)stream>>>(reward, bootstrap, out, T,
                                                                                               N, gamma);
+  CA_CUDA(cudaPeekAtLastError());
+  return CA_OK;
+}
+
+int ca_ga3c_record(const ca_ga3c_buffers* b, int64_t t, int32_t ring_slots, int32_t num_slots, int32_t agents_per_world,
+                   int32_t obs_len, int32_t time_max, float gamma, const int32_t* actions, const float* values,
+                   const float* reward, const uint8_t* done, const uint8_t* game_over, int device, void* stream) {
+  if (!b || !actions || !values || !reward || !done || !game_over) return fail(CA_ERR_INVALID_ARG, "NULL argument");
+  if (!b->obs_ring || !b->act_ring || !b->rew_ring || !b->length || !b->tcount || !b->done_trained || !b->out_x ||
+      !b->out_r || !b->out_a || !b->out_count)
+    return fail(CA_ERR_INVALID_ARG, "NULL buffer in ca_ga3c_buffers");
+  if (t < 0 || num_slots < 1 || agents_per_world < 1 || num_slots % agents_per_world != 0 || obs_len < 2 || time_max < 1 ||
+      ring_slots < time_max + 2 || b->capacity < 1)
+    return fail(CA_ERR_INVALID_ARG, "bad sizes (need ring_slots >= time_max + 2, num_slots %% agents_per_world == 0)");
+  DeviceGuard guard(device);
+  if (!guard.ok) return fail(CA_ERR_CUDA, "cudaSetDevice(%d) failed", device);
+  ca::Ga3cParams p;
+  p.b = *b; p.t = t; p.R = ring_slots; p.N = num_slots; p.A = agents_per_world; p.L = obs_len; p.time_max = time_max;
+  p.gamma = gamma; p.actions = actions; p.values = values; p.reward = reward; p.done = done; p.over = game_over;
+  const int threads = 128;
+  ca::ga3c_record_kernel<<<(num_slots + threads - 1) / threads, threads, 0, (cudaStream_t)stream>>>(p);
+  CA_CUDA(cudaPeekAtLastError());
+  return CA_OK;
+}
+
+int ca_ga3c_episode_stats(const float* obs_now, const float* reward, const uint8_t* game_over, float* ep_reward,
+                          int32_t* ep_steps, double* stats, int32_t num_worlds, int32_t agents_per_world,
+                          int32_t obs_len, int device, void* stream) {
+  if (!obs_now || !reward || !game_over || !ep_reward || !ep_steps || !stats || num_worlds < 1 || agents_per_world < 1)
+    return fail(CA_ERR_INVALID_ARG, "bad argument");
+  DeviceGuard guard(device);
+  if (!guard.ok) return fail(CA_ERR_CUDA, "cudaSetDevice(%d) failed", device);
+  const int threads = 128;
+  ca::ga3c_episode_stats_kernel<<<(num_worlds + threads - 1) / threads, threads, 0, (cudaStream_t)stream>>>(
+      obs_now, reward, game_over, ep_reward, ep_steps, stats, num_worlds, agents_per_world, obs_len);
   CA_CUDA(cudaPeekAtLastError());
   return CA_OK;
 }

@@ -1,0 +1,262 @@
+"""Policy/value network of GA3C-CADRL in PyTorch, with the reference's interface.
+
+Reference: `NetworkVP_rnn._create_graph` (GA3C/NetworkVP_rnn.py:39-108) + `NetworkVPCore` outputs, loss and
+optimiser (GA3C/NetworkVPCore.py:60-123,160-248), TensorFlow 1.15:
+  x_n = (x - AVG) / STD; seq_len = x[:, 0] (raw num_other_agents); host = x_n[:, 1:5]; others = x_n[:, 5:] as
+  (B, M, 7) -> tf.nn.dynamic_rnn(LSTMCell(64), sequence_length=seq_len) -> final h -> concat(host, h) ->
+  Dense256 ReLU (layer1) -> Dense256 ReLU (layer2) -> Dense256 ReLU (fullyconnected1) -> {logits_p(11) softmax,
+  logits_v(1)}.
+TF1 `LSTMCell` semantics are kept so that reference checkpoints map one to one: a single kernel
+[(7+64), 4*64] applied to concat(x_t, h), gate order i, j, f, o, forget bias 1.0:
+  c' = sigmoid(f + 1) * c + sigmoid(i) * tanh(j);  h' = sigmoid(o) * tanh(c');
+rows whose sequence ended (t >= seq_len) keep their state.  Parameter names follow the TF variable names
+(`rnn/lstm_cell/kernel`, `layer1/kernel`, ...).  The A3C loss uses sums, not means (NetworkVPCore.py:71-98);
+Adam follows TF's formulation (epsilon outside the bias-corrected sqrt).
+"""
+import math
+import os
+import re
+
+import torch
+
+from .Config import get_config
+
+
+def _glorot_uniform(fan_in, fan_out, generator):
+    limit = math.sqrt(6.0 / (fan_in + fan_out))
+    return (torch.rand(fan_in, fan_out, generator=generator) * 2 - 1) * limit
+
+
+class PolicyValueNet(torch.nn.Module):
+    """The function only (no optimiser): x [B, NN_INPUT_SIZE] float32 -> (softmax_p [B, num_actions], v [B])."""
+
+    HIDDEN = 64
+
+    def __init__(self, cfg, num_actions, seed=0):
+        super().__init__()
+        self.M = cfg.MAX_NUM_OTHER_AGENTS_OBSERVED
+        self.other_len = cfg.OTHER_AGENT_FULL_OBSERVATION_LENGTH
+        self.host_len = cfg.HOST_AGENT_STATE_SIZE
+        self.first = cfg.FIRST_STATE_INDEX
+        self.normalize = bool(cfg.NORMALIZE_INPUT)
+        self.min_policy = float(cfg.MIN_POLICY)
+        self.num_actions = num_actions
+        g = torch.Generator().manual_seed(seed)
+        H = self.HIDDEN
+        P = torch.nn.Parameter
+        # TF variable name -> parameter (kernels are [in, out] like TF); '/' becomes '__' in the torch names
+        shapes = [("rnn/lstm_cell", self.other_len + H, 4 * H), ("layer1", self.host_len + H, 256), ("layer2", 256, 256),
+                  ("fullyconnected1", 256, 256), ("logits_p", 256, num_actions), ("logits_v", 256, 1)]
+        self.params = torch.nn.ParameterDict()
+        for name, fan_in, fan_out in shapes:
+            self.params[(name + "/kernel").replace("/", "__")] = P(_glorot_uniform(fan_in, fan_out, g))
+            self.params[(name + "/bias").replace("/", "__")] = P(torch.zeros(fan_out))
+        self.register_buffer("avg", torch.tensor(cfg.NN_INPUT_AVG_VECTOR, dtype=torch.float32))
+        self.register_buffer("std", torch.tensor(cfg.NN_INPUT_STD_VECTOR, dtype=torch.float32))
+
+    def w(self, tf_name):
+        return self.params[tf_name.replace("/", "__")]
+
+    def tf_variables(self):
+        """{TF variable name: numpy array} (for checkpoint exchange and the NumPy oracle)."""
+        return {k.replace("__", "/"): v.detach().cpu().numpy() for k, v in self.params.items()}
+
+    def load_tf_variables(self, variables):
+        with torch.no_grad():
+            for name, value in variables.items():
+                self.w(name).copy_(torch.as_tensor(value, dtype=torch.float32))
+
+    def features(self, x):
+        H = self.HIDDEN
+        xn = (x - self.avg) / self.std if self.normalize else x
+        seq_len = x[:, 0]
+        host = xn[:, self.first:self.first + self.host_len]
+        others = xn[:, self.first + self.host_len:].reshape(-1, self.M, self.other_len)
+        B = x.shape[0]
+        h = x.new_zeros((B, H))
+        c = x.new_zeros((B, H))
+        K, b = self.w("rnn/lstm_cell/kernel"), self.w("rnn/lstm_cell/bias")
+        Kx, Kh = K[:self.other_len], K[self.other_len:]
+        for t in range(self.M):
+            z = others[:, t] @ Kx + h @ Kh + b
+            i, j, f, o = z.split(H, dim=1)
+            c_new = torch.sigmoid(f + 1.0) * c + torch.sigmoid(i) * torch.tanh(j)
+            h_new = torch.sigmoid(o) * torch.tanh(c_new)
+            live = (seq_len > t).unsqueeze(1)
+            c = torch.where(live, c_new, c)
+            h = torch.where(live, h_new, h)
+        l1_in = torch.cat([host, h], dim=1)
+        l1 = torch.relu(l1_in @ self.w("layer1/kernel") + self.w("layer1/bias"))
+        l2 = torch.relu(l1 @ self.w("layer2/kernel") + self.w("layer2/bias"))
+        return torch.relu(l2 @ self.w("fullyconnected1/kernel") + self.w("fullyconnected1/bias"))
+
+    def forward(self, x):
+        fc1 = self.features(x)
+        logits_p = fc1 @ self.w("logits_p/kernel") + self.w("logits_p/bias")
+        v = (fc1 @ self.w("logits_v/kernel") + self.w("logits_v/bias")).squeeze(1)
+        p = (torch.softmax(logits_p, dim=1) + self.min_policy) / (1.0 + self.min_policy * self.num_actions)
+        return p, v, logits_p
+
+
+class TFAdam(object):
+    """tf.train.AdamOptimizer update rule (beta1 .9, beta2 .999, eps 1e-8):
+    lr_t = lr * sqrt(1 - b2^t) / (1 - b1^t);  var -= lr_t * m / (sqrt(v) + eps)."""
+
+    def __init__(self, params, beta1=0.9, beta2=0.999, eps=1e-8):
+        self.params = [p for p in params]
+        self.b1, self.b2, self.eps = beta1, beta2, eps
+        self.m = [torch.zeros_like(p) for p in self.params]
+        self.v = [torch.zeros_like(p) for p in self.params]
+        self.t = 0
+
+    @torch.no_grad()
+    def step(self, lr):
+        self.t += 1
+        lr_t = lr * math.sqrt(1.0 - self.b2 ** self.t) / (1.0 - self.b1 ** self.t)
+        grads = [p.grad for p in self.params]
+        torch._foreach_mul_(self.m, self.b1)
+        torch._foreach_add_(self.m, grads, alpha=1.0 - self.b1)
+        torch._foreach_mul_(self.v, self.b2)
+        torch._foreach_addcmul_(self.v, grads, grads, value=1.0 - self.b2)
+        denom = torch._foreach_sqrt(self.v)
+        torch._foreach_add_(denom, self.eps)
+        torch._foreach_addcdiv_(self.params, self.m, denom, value=-lr_t)
+
+    def state_dict(self):
+        return {"m": self.m, "v": self.v, "t": self.t}
+
+    def load_state_dict(self, sd):
+        for dst, src in zip(self.m, sd["m"]):
+            dst.copy_(src)
+        for dst, src in zip(self.v, sd["v"]):
+            dst.copy_(src)
+        self.t = int(sd["t"])
+
+
+class NetworkVP_rnn(object):
+    """Interface of GA3C/NetworkVPCore.py:151-268: predict_p_and_v / predict_p / predict_v / predict_single /
+    train / log / save / load / get_global_step / get_variables_names / get_variable_value."""
+
+    def __init__(self, device, model_name, num_actions, seed=0):
+        cfg = get_config()
+        self.cfg = cfg
+        if isinstance(device, str) and device.startswith('/'):  # TF style '/cpu:0', '/gpu:0'
+            m = re.match(r"/(cpu|gpu):(\d+)", device)
+            device = "cpu" if m.group(1) == "cpu" else "cuda:%s" % m.group(2)
+        self.device = torch.device(device)
+        self.model_name = model_name
+        self.num_actions = num_actions
+        self.learning_rate_rl = cfg.LEARNING_RATE_RL_START
+        self.learning_rate = cfg.LEARNING_RATE_RL_START
+        self.beta = cfg.BETA_START
+        self.log_epsilon = cfg.LOG_EPSILON
+        self.net = PolicyValueNet(cfg, num_actions, seed=seed).to(self.device)
+        self.opt = TFAdam(self.net.parameters())
+        self.global_step = 0
+        self.checkpoints_save_dir = os.environ.get(
+            "GA3C_CHECKPOINT_DIR", os.path.join(os.getcwd(), "checkpoints", "RL_tmp"))
+        self.last_costs = {}
+
+    # ---- prediction (GA3C/NetworkVPCore.py:160-176)
+    def _as_input(self, x):
+        return torch.as_tensor(x, dtype=torch.float32, device=self.device)
+
+    @torch.no_grad()
+    def predict_p_and_v_device(self, x):
+        """Device tensors in and out (used by the on-GPU rollout): x [B, NN_INPUT_SIZE] -> p [B, 11], v [B]."""
+        p, v, _ = self.net(x)
+        return p, v
+
+    def predict_p_and_v(self, x):
+        p, v = self.predict_p_and_v_device(self._as_input(x))
+        return p.cpu().numpy(), v.cpu().numpy()
+
+    def predict_p(self, x):
+        return self.predict_p_and_v(x)[0]
+
+    def predict_v(self, x):
+        return self.predict_p_and_v(x)[1]
+
+    def predict_single(self, x):
+        return self.predict_p(x[None, :])[0]
+
+    # ---- A3C loss (GA3C/NetworkVPCore.py:64-98)
+    def losses(self, x, y_r, action_index):
+        """action_index: one-hot float [B, num_actions] (reference layout) or int64 [B] action ids."""
+        p, v, _ = self.net(x)
+        if action_index.dim() == 2:
+            sel = (p * action_index).sum(dim=1)
+        else:
+            sel = p.gather(1, action_index.long().unsqueeze(1)).squeeze(1)
+        cost_v = 0.5 * ((y_r - v) ** 2).sum()
+        cost_p_advant = torch.log(torch.clamp(sel, min=self.log_epsilon)) * (y_r - v.detach())
+        cost_p_entrop = -1.0 * self.beta * (torch.log(torch.clamp(p, min=self.log_epsilon)) * p).sum(dim=1)
+        cost_p = -(cost_p_advant.sum() + cost_p_entrop.sum())
+        return {"cost_all": cost_p + cost_v, "cost_p": cost_p, "cost_v": cost_v,
+                "cost_p_advant_agg": cost_p_advant.sum(), "cost_p_entrop_agg": cost_p_entrop.sum()}
+
+    def train(self, x, y_r, a, trainer_id=0, learning_method='RL'):
+        if learning_method != 'RL':
+            raise NotImplementedError("regression pre-training is out of scope (datasets are git-LFS pointers)")
+        x = self._as_input(x)
+        y_r = self._as_input(y_r)
+        a = torch.as_tensor(a, device=self.device)
+        costs = self.losses(x, y_r, a)
+        for p in self.net.parameters():
+            p.grad = None
+        costs["cost_all"].backward()
+        if self.cfg.USE_GRAD_CLIP:
+            for p in self.net.parameters():  # tf.clip_by_average_norm
+                avg_norm = p.grad.norm() / p.grad.numel()
+                p.grad.mul_(torch.clamp(self.cfg.GRAD_CLIP_NORM / (avg_norm + 1e-12), max=1.0))
+        self.opt.step(self.learning_rate)
+        self.global_step += 1
+        self.last_costs = costs
+        return costs
+
+    def get_global_step(self):
+        return self.global_step
+
+    def log(self, x, y_r, a, reward, roll_reward, episode):
+        c = {k: float(v) for k, v in self.last_costs.items()}
+        print("[NetworkVP] step %d episode %d reward %.4f roll_reward %.4f %s" % (self.global_step, episode, reward, roll_reward, c))
+
+    # ---- checkpoints: same file naming as GA3C/NetworkVPCore.py:219-248 ('<model_name>_%08d')
+    def _checkpoint_filename(self, episode, mode='save', learning_method='RL', wandb_runid_for_loading=None):
+        d = self.checkpoints_save_dir
+        if mode == 'load' and wandb_runid_for_loading is not None:
+            d = os.path.join(os.path.dirname(self.checkpoints_save_dir), learning_method, 'wandb', wandb_runid_for_loading,
+                             'checkpoints')
+        return os.path.join(d, '%s_%08d' % (self.model_name, episode))
+
+    @staticmethod
+    def _get_episode_from_filename(filename):
+        return int(re.split(r'/|_|\.', filename)[-2 if filename.endswith('.pt') else -1])
+
+    def save(self, episode, learning_method='RL'):
+        path = self._checkpoint_filename(episode, mode='save', learning_method=learning_method) + ".pt"
+        os.makedirs(os.path.dirname(path), exist_ok=True)
+        torch.save({"variables": {k: torch.as_tensor(v) for k, v in self.net.tf_variables().items()},
+                    "adam": self.opt.state_dict(), "step": self.global_step, "episode": episode}, path)
+        return path
+
+    def load(self, learning_method='RL', path=None):
+        if path is None:
+            d = self.checkpoints_save_dir
+            cands = sorted(f for f in (os.listdir(d) if os.path.isdir(d) else []) if f.startswith(self.model_name + "_"))
+            if not cands:
+                raise FileNotFoundError("no checkpoint '%s_*' in %s" % (self.model_name, d))
+            ep = self.cfg.EPISODE_NUMBER_TO_LOAD if getattr(self.cfg, 'EPISODE_NUMBER_TO_LOAD', 0) > 0 else None
+            path = os.path.join(d, ('%s_%08d.pt' % (self.model_name, ep)) if ep else cands[-1])
+        print("[NetworkVPCore] Loading checkpoint file:", path)
+        ck = torch.load(path, map_location=self.device)
+        self.net.load_tf_variables(ck["variables"])
+        self.opt.load_state_dict(ck["adam"])
+        self.global_step = int(ck["step"])
+        return int(ck.get("episode", self._get_episode_from_filename(path)))
+
+    def get_variables_names(self):
+        return [k + ":0" for k in self.net.tf_variables()]
+
+    def get_variable_value(self, name):
+        return self.net.tf_variables()[name.split(":")[0]]

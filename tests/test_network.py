@@ -1,0 +1,115 @@
+"""CPU: the PyTorch NetworkVP_rnn against the NumPy oracle written from the TF-1.15 LSTMCell / dense definitions
+(oracle/network_oracle.py); loss values; TF-style Adam; checkpoint round trip; Config parity with the values the
+reference computes."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import network_oracle
+from rl_collision_avoidance_b200.ga3c import Config as cfgmod
+from rl_collision_avoidance_b200.ga3c.NetworkVP_rnn import NetworkVP_rnn, TFAdam
+
+
+@pytest.fixture(params=["TrainPhase1", "TrainPhase2"])
+def cfg(request):
+    c = getattr(cfgmod, request.param)()
+    cfgmod.set_config(c)
+    yield c
+    cfgmod.set_config(None)
+
+
+def _random_obs(cfg, B, rng):
+    M = cfg.MAX_NUM_OTHER_AGENTS_OBSERVED
+    x = rng.normal(size=(B, cfg.NN_INPUT_SIZE)).astype(np.float32)
+    x[:, 0] = rng.integers(0, M + 1, B)          # raw num_other_agents drives the LSTM sequence length
+    x[:, 1] = np.abs(x[:, 1]) * 5
+    return x
+
+
+def test_config_values_match_reference(cfg):
+    M = cfg.MAX_NUM_OTHER_AGENTS_OBSERVED
+    assert cfg.NN_INPUT_SIZE == 5 + 7 * M and cfg.TIME_MAX == 20 and cfg.DISCOUNT == 0.97 and cfg.NUM_ACTIONS == 11
+    np.testing.assert_allclose(cfg.NN_INPUT_AVG_VECTOR[:5], [1.0, 0.0, 0.0, 1.0, 0.5])
+    np.testing.assert_allclose(cfg.NN_INPUT_STD_VECTOR[:5], [1.0, 5.0, 3.14, 1.0, 1.0], rtol=1e-6)
+    np.testing.assert_allclose(cfg.NN_INPUT_AVG_VECTOR[5:12], [0.0, 0.0, 0.0, 0.0, 0.5, 0.0, 1.0])
+    np.testing.assert_allclose(cfg.NN_INPUT_STD_VECTOR[5:12], [5.0, 5.0, 1.0, 1.0, 1.0, 5.0, 1.0])
+    assert cfg.LEARNING_RATE_RL_START == 2e-5 and cfg.BETA_START == 1e-4 and cfg.LOG_EPSILON == 1e-6
+
+
+def test_forward_matches_numpy_oracle(cfg):
+    rng = np.random.default_rng(0)
+    net = NetworkVP_rnn("/cpu:0", "network", 11, seed=3)
+    # non-trivial biases so the forget-bias / gate-order conventions are exercised
+    with torch.no_grad():
+        for name, p in net.net.params.items():
+            if name.endswith("bias"):
+                p.copy_(torch.from_numpy(rng.normal(scale=0.3, size=tuple(p.shape)).astype(np.float32)))
+    x = _random_obs(cfg, 257, rng)
+    p, v = net.predict_p_and_v(x)
+    p_ref, v_ref = network_oracle.forward(net.net.tf_variables(), x, cfg.NN_INPUT_AVG_VECTOR, cfg.NN_INPUT_STD_VECTOR,
+                                          cfg.MAX_NUM_OTHER_AGENTS_OBSERVED)
+    assert p.shape == (257, 11) and v.shape == (257,)
+    np.testing.assert_allclose(p, p_ref, rtol=0, atol=2e-6)
+    np.testing.assert_allclose(v, v_ref, rtol=0, atol=2e-5)
+    np.testing.assert_allclose(p.sum(axis=1), 1.0, atol=1e-5)
+    # rows with zero other agents must not depend on the other-agent columns at all
+    x0 = x.copy(); x0[:, 0] = 0
+    xa = x0.copy(); xa[:, 5:] = 123.0
+    np.testing.assert_array_equal(net.predict_p_and_v(x0)[0], net.predict_p_and_v(xa)[0])
+    assert net.predict_single(x[0]).shape == (11,)
+
+
+def test_loss_and_adam_step(cfg):
+    rng = np.random.default_rng(1)
+    net = NetworkVP_rnn("cpu", "network", 11, seed=1)
+    B = 120
+    x = _random_obs(cfg, B, rng)
+    y = rng.normal(size=B).astype(np.float32)
+    a_idx = rng.integers(0, 11, B)
+    a = np.eye(11, dtype=np.float32)[a_idx]
+    p_ref, v_ref = network_oracle.forward(net.net.tf_variables(), x, cfg.NN_INPUT_AVG_VECTOR, cfg.NN_INPUT_STD_VECTOR,
+                                          cfg.MAX_NUM_OTHER_AGENTS_OBSERVED)
+    ref_all, ref_p, ref_v = network_oracle.a3c_costs(p_ref, v_ref, y, a, beta=net.beta)
+    before = {k: v.copy() for k, v in net.net.tf_variables().items()}
+    costs = net.train(x, y, a, 0)
+    assert abs(float(costs["cost_all"].detach()) - ref_all) < 1e-3 * max(1.0, abs(ref_all))
+    assert abs(float(costs["cost_v"].detach()) - ref_v) < 1e-3 * max(1.0, abs(ref_v))
+    # int action ids are accepted too and give the same loss
+    net2 = NetworkVP_rnn("cpu", "network", 11, seed=1)
+    c2 = net2.train(x, y, a_idx, 0)
+    assert abs(float(c2["cost_all"].detach()) - float(costs["cost_all"].detach())) < 1e-4
+    # first Adam step: every touched weight moves by ~lr (|m/sqrt(v)| = 1 at t = 1)
+    after = net.net.tf_variables()
+    d = np.abs(after["layer2/kernel"] - before["layer2/kernel"])
+    assert d.max() <= 2e-5 * 1.001 and np.median(d[d > 0]) > 1.9e-5
+    assert net.get_global_step() == 1
+
+
+def test_tf_adam_rule():
+    w = torch.nn.Parameter(torch.tensor([1.0, -2.0]))
+    opt = TFAdam([w])
+    m = v = np.zeros(2); x = np.array([1.0, -2.0])
+    for t in range(1, 6):
+        g = np.array([0.5 * t, -0.1])
+        w.grad = torch.tensor(g, dtype=torch.float32)
+        opt.step(1e-2)
+        m = 0.9 * m + 0.1 * g; v = 0.999 * v + 0.001 * g * g
+        x = x - 1e-2 * np.sqrt(1 - 0.999 ** t) / (1 - 0.9 ** t) * m / (np.sqrt(v) + 1e-8)
+    np.testing.assert_allclose(w.detach().numpy(), x, rtol=1e-5)
+
+
+def test_checkpoint_round_trip(cfg, tmp_path, monkeypatch):
+    monkeypatch.setenv("GA3C_CHECKPOINT_DIR", str(tmp_path))
+    rng = np.random.default_rng(2)
+    a = NetworkVP_rnn("cpu", "network", 11, seed=5)
+    x = _random_obs(cfg, 64, rng)
+    a.train(x, rng.normal(size=64).astype(np.float32), rng.integers(0, 11, 64), 0)
+    path = a.save(1234)
+    assert path.endswith("network_00001234.pt")
+    b = NetworkVP_rnn("cpu", "network", 11, seed=99)
+    assert b.load(path=path) == 1234
+    if cfg.EPISODE_NUMBER_TO_LOAD == 0:
+        assert b.load() == 1234      # newest '<model_name>_*' in the checkpoint directory
+    np.testing.assert_array_equal(a.predict_p_and_v(x)[0], b.predict_p_and_v(x)[0])
+    assert b.get_global_step() == 1
+    assert "rnn/lstm_cell/kernel:0" in b.get_variables_names()
