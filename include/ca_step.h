@@ -149,6 +149,11 @@ int ca_destroy(ca_env* env);
  * on_device != 0: both pointers are device pointers (copied stream-ordered on `stream`). */
 int ca_set_world_state(ca_env* env, const double* init, const int32_t* num_agents, int on_device, void* stream);
 
+/* Replace only the reset snapshot (same tensors as ca_set_world_state): live worlds keep running and pick the new
+ * scenario — which may have a different agent count — up at their next reset / auto-reset.  This is how fresh
+ * scenarios are streamed in (≙ test_case_fn being called again on every env.reset(), collision_avoidance_env.py:283). */
+int ca_set_reset_state(ca_env* env, const double* init, const int32_t* num_agents, int on_device, void* stream);
+
 /* Reset worlds to their injected initial state (world_mask: device uint8[W], NULL = all) and write the
  * first observation of every world (unmasked worlds: their current observation) to obs (device float[W][A][L]);
  * sorted_idx (device int32[W][A][M], may be NULL) receives the neighbour order (-1 = empty slot). */

@@ -41,7 +41,8 @@ typedef struct ca_oracle {
   int W, A, M, L;
   agent_t* agents;      /* [W][A] */
   agent_t* init_agents; /* [W][A] snapshot for reset */
-  int32_t* n;           /* [W] */
+  int32_t* n;           /* [W] live agent count */
+  int32_t* n0;          /* [W] agent count of the reset snapshot */
   int initialised;
 } ca_oracle;
 
@@ -242,6 +243,7 @@ static void observe_world(const ca_oracle* o, int w, double* obs, int32_t* sorte
 }
 
 static void reset_world(ca_oracle* o, int w) {
+  o->n[w] = o->n0[w];
   memcpy(o->agents + (size_t)w * o->A, o->init_agents + (size_t)w * o->A, sizeof(agent_t) * o->A);
 }
 
@@ -380,22 +382,23 @@ int ca_oracle_create(const ca_config* cfg, ca_oracle** out) {
   o->agents = (agent_t*)calloc((size_t)o->W * o->A, sizeof(agent_t));
   o->init_agents = (agent_t*)calloc((size_t)o->W * o->A, sizeof(agent_t));
   o->n = (int32_t*)calloc((size_t)o->W, sizeof(int32_t));
-  if (!o->agents || !o->init_agents || !o->n) return CA_ERR_ALLOC;
+  o->n0 = (int32_t*)calloc((size_t)o->W, sizeof(int32_t));
+  if (!o->agents || !o->init_agents || !o->n || !o->n0) return CA_ERR_ALLOC;
   *out = o;
   return CA_OK;
 }
 
 void ca_oracle_destroy(ca_oracle* o) {
   if (!o) return;
-  free(o->agents); free(o->init_agents); free(o->n); free(o);
+  free(o->agents); free(o->init_agents); free(o->n); free(o->n0); free(o);
 }
 
 /* Agent.__init__/reset, GCA/envs/agent.py:29-136 */
-int ca_oracle_set_world_state(ca_oracle* o, const double* init, const int32_t* num_agents) {
+static int load_snapshot(ca_oracle* o, const double* init, const int32_t* num_agents) {
   for (int w = 0; w < o->W; ++w) {
     int n = num_agents[w];
     if (n < 1 || n > o->A) return CA_ERR_INVALID_ARG;
-    o->n[w] = n;
+    o->n0[w] = n;
     for (int i = 0; i < o->A; ++i) {
       agent_t* a = &o->init_agents[(size_t)w * o->A + i];
       memset(a, 0, sizeof(*a));
@@ -413,9 +416,22 @@ int ca_oracle_set_world_state(ca_oracle* o, const double* init, const int32_t* n
       update_ego_frame(a);
     }
   }
+  return CA_OK;
+}
+
+int ca_oracle_set_world_state(ca_oracle* o, const double* init, const int32_t* num_agents) {
+  int rc = load_snapshot(o, init, num_agents);
+  if (rc != CA_OK) return rc;
   memcpy(o->agents, o->init_agents, sizeof(agent_t) * (size_t)o->W * o->A);
+  memcpy(o->n, o->n0, sizeof(int32_t) * (size_t)o->W);
   o->initialised = 1;
   return CA_OK;
+}
+
+/* only the reset snapshot changes; live worlds pick it up at their next reset (≙ test_case_fn on env.reset()) */
+int ca_oracle_set_reset_state(ca_oracle* o, const double* init, const int32_t* num_agents) {
+  if (!o->initialised) return CA_ERR_NOT_INITIALISED;
+  return load_snapshot(o, init, num_agents);
 }
 
 int ca_oracle_reset(ca_oracle* o, const uint8_t* world_mask, double* obs, int32_t* sorted_idx) {

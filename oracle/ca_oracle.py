@@ -39,6 +39,7 @@ def lib():
         L.ca_oracle_destroy.restype = None
         L.ca_oracle_set_world_state.argtypes = [vp, vp, vp]
         L.ca_oracle_reset.argtypes = [vp, vp, vp, vp]
+        L.ca_oracle_set_reset_state.argtypes = [vp, vp, vp]
         L.ca_oracle_step.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, C.c_int]
         L.ca_oracle_get_state.argtypes = [vp, vp]
         L.ca_oracle_nstep_returns.argtypes = [vp, vp, vp, C.c_int, C.c_int, C.c_double]
@@ -87,6 +88,14 @@ class OracleEnv(object):
         rc = lib().ca_oracle_set_world_state(self._h, _p(init), _p(num_agents))
         if rc != 0:
             raise RuntimeError("ca_oracle_set_world_state failed: %d" % rc)
+
+    def set_reset_state(self, init, num_agents):
+        init = np.ascontiguousarray(init, dtype=np.float64)
+        num_agents = np.ascontiguousarray(num_agents, dtype=np.int32)
+        assert init.shape == (self.W, self.A, _abi.INIT_STRIDE), init.shape
+        rc = lib().ca_oracle_set_reset_state(self._h, _p(init), _p(num_agents))
+        if rc != 0:
+            raise RuntimeError("ca_oracle_set_reset_state failed: %d" % rc)
 
     def reset(self, world_mask=None):
         m = None if world_mask is None else np.ascontiguousarray(world_mask, dtype=np.uint8)

@@ -24,7 +24,7 @@ NVCC_FLAGS = [
 
 # every symbol include/ca_step.h declares
 EXPORTS = [
-    "ca_default_config", "ca_create", "ca_destroy", "ca_set_world_state", "ca_reset", "ca_step", "ca_step_host",
+    "ca_default_config", "ca_create", "ca_destroy", "ca_set_world_state", "ca_set_reset_state", "ca_reset", "ca_step", "ca_step_host",
     "ca_reset_host", "ca_get_state", "ca_launch_count", "ca_host_alloc", "ca_host_free", "ca_nstep_returns",
     "ca_ga3c_record", "ca_ga3c_episode_stats",
     "ca_strerror", "ca_last_error", "ca_abi_version",
@@ -79,6 +79,7 @@ def lib():
     L.ca_create.argtypes = [C.POINTER(_abi.CaConfig), C.POINTER(vp)]
     L.ca_destroy.argtypes = [vp]
     L.ca_set_world_state.argtypes = [vp, vp, vp, C.c_int, vp]
+    L.ca_set_reset_state.argtypes = [vp, vp, vp, C.c_int, vp]
     L.ca_reset.argtypes = [vp, vp, vp, vp, vp]
     L.ca_step.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp]
     L.ca_step_host.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp]

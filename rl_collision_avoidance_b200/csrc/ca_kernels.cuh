@@ -42,7 +42,8 @@ struct Params {
   double dt, thr_sq, close_range, r_goal, r_coll, r_step, r_min, r_max, max_heading_change, sensing_horizon;
   StateArrays s;        // live state
   StateArrays s0;       // snapshot injected by ca_set_world_state (for reset)
-  const int32_t* nag;   // [W]
+  int32_t* nag;         // [W] live agent count per world
+  const int32_t* nag0;  // [W] agent count of the reset snapshot (a world may come back with a different count)
   // I/O (device)
   const int32_t* actions;  // [W*A]
   const double* cont;      // [W*A*2] or null
@@ -334,8 +335,8 @@ __global__ void __launch_bounds__(kBlock) ca_world_kernel(const __grid_constant_
   const long first_world_cta = (long)blockIdx.x * kWarps * p.wpw;
   const long w = first_world_cta + (long)warp * p.wpw + wl;
   const bool world_ok = wl < p.wpw && w < p.W;
-  const int n = world_ok ? p.nag[w] : 0;
-  const bool valid = world_ok && i < n;
+  int n = world_ok ? p.nag[w] : 0;
+  bool valid = world_ok && i < n;
   const size_t g = world_ok ? (size_t)w * A + i : 0;
   const unsigned gmask = (A >= 32 ? kFull : ((1u << A) - 1u)) << (base & 31);
 
@@ -447,7 +448,10 @@ __global__ void __launch_bounds__(kBlock) ca_world_kernel(const __grid_constant_
   if (!kStep || __any_sync(kFull, do_reset)) {
     const bool again = kStep ? do_reset : true;  // this lane (re)computes its observation
     if (do_reset) {
-      if (valid) load_agent(p.s0, g, a);
+      n = p.nag0[w];
+      valid = i < n;
+      if (i == 0) p.nag[w] = n;
+      if (valid) load_agent(p.s0, g, a); else zero_agent(a);
       e = ego_frame(a.px, a.py, a.gx, a.gy, a.hd);
     }
     bool c_unused;
@@ -457,13 +461,12 @@ __global__ void __launch_bounds__(kBlock) ca_world_kernel(const __grid_constant_
   }
 
   // ---- state write-back (coalesced; goal only changes for static agents / on reset)
-  if (valid) {
+  if ((valid && kStep) || do_reset) {  // a reset rewrites every slot of the world (the scenario may have changed)
     StateArrays s = p.s;
-    if (kStep || do_reset) {
-      s.px[g] = a.px; s.py[g] = a.py; s.hd[g] = a.hd; s.vx[g] = a.vx; s.vy[g] = a.vy; s.tr[g] = a.tr;
-      s.flags[g] = (uint8_t)a.flags;
-      if (do_reset || a.policy == CA_POLICY_STATIC) { s.gx[g] = a.gx; s.gy[g] = a.gy; }
-    }
+    s.px[g] = a.px; s.py[g] = a.py; s.hd[g] = a.hd; s.vx[g] = a.vx; s.vy[g] = a.vy; s.tr[g] = a.tr;
+    s.flags[g] = (uint8_t)a.flags;
+    if (do_reset || a.policy == CA_POLICY_STATIC) { s.gx[g] = a.gx; s.gy[g] = a.gy; }
+    if (do_reset) { s.rad[g] = a.rad; s.ps[g] = a.ps; s.policy[g] = (uint8_t)a.policy; }
   }
 
   store_tile(p, sm.tile, first_world_cta, tid);

@@ -61,7 +61,7 @@ struct ca_env {
   size_t smem_fast = 0;        // dynamic shared memory of the specialised step kernel (observation tile only)
   double* slab = nullptr;      // 20 double arrays of W*A: live state then snapshot
   uint8_t* bytes = nullptr;    // 4 uint8 arrays of W*A: flags, policy, flags0, policy0
-  int32_t* nag = nullptr;      // [W]
+  int32_t* nag = nullptr;      // [2][W]: live agent counts, then the snapshot's
   ca::StateArrays s{}, s0{};
   bool initialised = false;
   int64_t launches = 0;
@@ -84,14 +84,18 @@ using ca::kWarps;
 
 // init[W][A][CA_INIT_STRIDE] (AoS, float64) -> SoA snapshot + live state.  Agent.__init__/reset, agent.py:29-136.
 __global__ void unpack_init_kernel(const double* __restrict__ init, const int32_t* __restrict__ nag_in,
-                                   int32_t* __restrict__ nag, ca::StateArrays s, ca::StateArrays s0, int W, int A,
-                                   double max_time_ratio, double thr, double dt) {
+                                   int32_t* __restrict__ nag, int32_t* __restrict__ nag0, ca::StateArrays s,
+                                   ca::StateArrays s0, int W, int A, double max_time_ratio, double thr, double dt,
+                                   bool snapshot_only) {
   const long g = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (g >= (long)W * A) return;
   const int w = (int)(g / A), i = (int)(g - (long)w * A);
   int n = nag_in[w];
   n = n < 1 ? 1 : (n > A ? A : n);
-  if (i == 0) nag[w] = n;
+  if (i == 0) {
+    nag0[w] = n;
+    if (!snapshot_only) nag[w] = n;
+  }
   double v[CA_INIT_STRIDE];
 #pragma unroll
   for (int c = 0; c < CA_INIT_STRIDE; ++c) v[c] = i < n ? init[g * CA_INIT_STRIDE + c] : 0.0;
@@ -102,18 +106,14 @@ __global__ void unpack_init_kernel(const double* __restrict__ init, const int32_
     t0 = max_time_ratio * ((nrm - thr) / v[CA_I_PREF_SPEED]);
     if (!(t0 > dt)) t0 = dt;
   }
-  s0.px[g] = s.px[g] = v[CA_I_PX];
-  s0.py[g] = s.py[g] = v[CA_I_PY];
-  s0.hd[g] = s.hd[g] = v[CA_I_HEADING];
-  s0.vx[g] = s.vx[g] = 0.0;
-  s0.vy[g] = s.vy[g] = 0.0;
-  s0.tr[g] = s.tr[g] = i < n ? t0 : 0.0;
-  s0.gx[g] = s.gx[g] = v[CA_I_GX];
-  s0.gy[g] = s.gy[g] = v[CA_I_GY];
-  s0.rad[g] = s.rad[g] = v[CA_I_RADIUS];
-  s0.ps[g] = s.ps[g] = v[CA_I_PREF_SPEED];
-  s0.flags[g] = s.flags[g] = 0;
-  s0.policy[g] = s.policy[g] = (uint8_t)(int)v[CA_I_POLICY];
+  const double tr = i < n ? t0 : 0.0;
+  s0.px[g] = v[CA_I_PX]; s0.py[g] = v[CA_I_PY]; s0.hd[g] = v[CA_I_HEADING]; s0.vx[g] = 0.0; s0.vy[g] = 0.0; s0.tr[g] = tr;
+  s0.gx[g] = v[CA_I_GX]; s0.gy[g] = v[CA_I_GY]; s0.rad[g] = v[CA_I_RADIUS]; s0.ps[g] = v[CA_I_PREF_SPEED];
+  s0.flags[g] = 0; s0.policy[g] = (uint8_t)(int)v[CA_I_POLICY];
+  if (snapshot_only) return;
+  s.px[g] = v[CA_I_PX]; s.py[g] = v[CA_I_PY]; s.hd[g] = v[CA_I_HEADING]; s.vx[g] = 0.0; s.vy[g] = 0.0; s.tr[g] = tr;
+  s.gx[g] = v[CA_I_GX]; s.gy[g] = v[CA_I_GY]; s.rad[g] = v[CA_I_RADIUS]; s.ps[g] = v[CA_I_PREF_SPEED];
+  s.flags[g] = 0; s.policy[g] = (uint8_t)(int)v[CA_I_POLICY];
 }
 
 __global__ void pack_state_kernel(ca::StateArrays s, double* __restrict__ out, long total) {
@@ -151,7 +151,7 @@ ca::Params make_params(const ca_env* e) {
   p.r_min = c.min_possible_reward; p.r_max = c.max_possible_reward;
   p.max_heading_change = c.max_heading_change;
   p.sensing_horizon = c.sensing_horizon;
-  p.s = e->s; p.s0 = e->s0; p.nag = e->nag;
+  p.s = e->s; p.s0 = e->s0; p.nag = e->nag; p.nag0 = e->nag + e->W;
   return p;
 }
 
@@ -318,7 +318,7 @@ int ca_create(const ca_config* cfg, ca_env** out) {
   }
   const size_t n = (size_t)e->W * e->A;
   if (cudaMalloc(&e->slab, n * 20 * sizeof(double)) != cudaSuccess || cudaMalloc(&e->bytes, n * 4) != cudaSuccess ||
-      cudaMalloc(&e->nag, (size_t)e->W * sizeof(int32_t)) != cudaSuccess) {
+      cudaMalloc(&e->nag, (size_t)e->W * 2 * sizeof(int32_t)) != cudaSuccess) {
     cudaFree(e->slab); cudaFree(e->bytes); cudaFree(e->nag);
     delete e;
     cudaGetLastError();
@@ -341,7 +341,8 @@ int ca_destroy(ca_env* e) {
   return CA_OK;
 }
 
-int ca_set_world_state(ca_env* e, const double* init, const int32_t* num_agents, int on_device, void* stream) {
+static int set_state_impl(ca_env* e, const double* init, const int32_t* num_agents, int on_device, void* stream,
+                          bool snapshot_only) {
   if (!e || !init || !num_agents) return fail(CA_ERR_INVALID_ARG, "NULL argument");
   DeviceGuard guard(e->cfg.device);
   cudaStream_t st = (cudaStream_t)stream;
@@ -363,8 +364,8 @@ int ca_set_world_state(ca_env* e, const double* init, const int32_t* num_agents,
   }
   const int threads = 256;
   const int blocks = (int)((n + threads - 1) / threads);
-  unpack_init_kernel<<<blocks, threads, 0, st>>>(d_init, d_nag, e->nag, e->s, e->s0, e->W, e->A, e->cfg.max_time_ratio,
-                                                 e->cfg.near_goal_threshold, e->cfg.dt);
+  unpack_init_kernel<<<blocks, threads, 0, st>>>(d_init, d_nag, e->nag, e->nag + e->W, e->s, e->s0, e->W, e->A,
+                                                 e->cfg.max_time_ratio, e->cfg.near_goal_threshold, e->cfg.dt, snapshot_only);
   CA_CUDA(cudaPeekAtLastError());
   e->launches += 1;
   if (!on_device) {
@@ -372,8 +373,17 @@ int ca_set_world_state(ca_env* e, const double* init, const int32_t* num_agents,
     cudaFree(tmp_init);
     cudaFree(tmp_nag);
   }
-  e->initialised = true;
+  if (!snapshot_only) e->initialised = true;
   return CA_OK;
+}
+
+int ca_set_world_state(ca_env* e, const double* init, const int32_t* num_agents, int on_device, void* stream) {
+  return set_state_impl(e, init, num_agents, on_device, stream, false);
+}
+
+int ca_set_reset_state(ca_env* e, const double* init, const int32_t* num_agents, int on_device, void* stream) {
+  if (e && !e->initialised) return fail(CA_ERR_NOT_INITIALISED, "ca_set_reset_state before ca_set_world_state");
+  return set_state_impl(e, init, num_agents, on_device, stream, true);
 }
 
 int ca_reset(ca_env* e, const uint8_t* world_mask, float* obs, int32_t* sorted_idx, void* stream) {

@@ -173,8 +173,8 @@ __global__ void __launch_bounds__(kBlock) ca_step_kernel(const __grid_constant__
   const long first_world_warp = ((long)blockIdx.x * kWarps + warp) * wpw;
   const long w = first_world_warp + wl;
   const bool world_ok = wl < wpw && w < p.W;
-  const int n = world_ok ? p.nag[w] : 0;
-  const bool valid = world_ok && i < n;
+  int n = world_ok ? p.nag[w] : 0;
+  bool valid = world_ok && i < n;
   const size_t g = world_ok ? (size_t)w * kA + i : 0;
   const unsigned gmask = (kA >= 32 ? kFull : ((1u << kA) - 1u)) << (base & 31);
 
@@ -281,7 +281,10 @@ __global__ void __launch_bounds__(kBlock) ca_step_kernel(const __grid_constant__
     // DummyVecEnv semantics: worlds that finished reload their injected initial state and observe again;
     // the other worlds of the warp observe their post-step state.
     if (do_reset) {
-      if (valid) load_agent(p.s0, g, a);
+      n = p.nag0[w];
+      valid = i < n;
+      if (i == 0) p.nag[w] = n;
+      if (valid) load_agent(p.s0, g, a); else zero_agent(a);
       e = ego_frame(a.px, a.py, a.gx, a.gy, a.hd);
     }
     bool c_unused;
@@ -291,11 +294,12 @@ __global__ void __launch_bounds__(kBlock) ca_step_kernel(const __grid_constant__
   }
 
   // ---- state write-back
-  if (valid) {
+  if (valid || do_reset) {  // a reset rewrites every slot of the world (the new scenario may have fewer agents)
     StateArrays s = p.s;
     s.px[g] = a.px; s.py[g] = a.py; s.hd[g] = a.hd; s.vx[g] = a.vx; s.vy[g] = a.vy; s.tr[g] = a.tr;
     s.flags[g] = (uint8_t)a.flags;
     if (do_reset || a.policy == CA_POLICY_STATIC) { s.gx[g] = a.gx; s.gy[g] = a.gy; }
+    if (do_reset) { s.rad[g] = a.rad; s.ps[g] = a.ps; s.policy[g] = (uint8_t)a.policy; }
   }
 
   if (p.warp_store) fast_store_warp_tile<kA>(p, wtile, first_world_warp, lane);

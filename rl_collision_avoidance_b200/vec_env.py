@@ -56,8 +56,11 @@ class CaHandle(object):
         check(lib().ca_launch_count(self._h, C.byref(out)), "ca_launch_count")
         return out.value
 
-    def set_world_state(self, init_ptr, nag_ptr, on_device, stream=None):
-        check(lib().ca_set_world_state(self._h, init_ptr, nag_ptr, int(on_device), stream), "ca_set_world_state")
+    def set_world_state(self, init_ptr, nag_ptr, on_device, stream=None, snapshot_only=False):
+        if snapshot_only:
+            check(lib().ca_set_reset_state(self._h, init_ptr, nag_ptr, int(on_device), stream), "ca_set_reset_state")
+        else:
+            check(lib().ca_set_world_state(self._h, init_ptr, nag_ptr, int(on_device), stream), "ca_set_world_state")
 
     def get_state_host(self):
         out = np.zeros((self.W, self.A, _abi.STATE_STRIDE), dtype=np.float64)
@@ -133,14 +136,18 @@ class HostVecEnv(object):
     def d2h_bytes_per_step(self):
         return self.obs.nbytes + self.reward.nbytes + self.done.nbytes + self.game_over.nbytes
 
-    def set_world_state(self, init, num_agents):
+    def set_world_state(self, init, num_agents, snapshot_only=False):
         init = np.ascontiguousarray(init, dtype=np.float64)
         num_agents = np.ascontiguousarray(num_agents, dtype=np.int32)
         if init.shape != (self.W, self.A, _abi.INIT_STRIDE):
             raise ValueError("init must have shape %s, got %s" % ((self.W, self.A, _abi.INIT_STRIDE), init.shape))
         if num_agents.shape != (self.W,):
             raise ValueError("num_agents must have shape (%d,)" % self.W)
-        self.handle.set_world_state(_vp(init), _vp(num_agents), False)
+        self.handle.set_world_state(_vp(init), _vp(num_agents), False, snapshot_only=snapshot_only)
+
+    def set_reset_state(self, init, num_agents):
+        """New scenarios that worlds pick up at their next reset / auto-reset (ca_set_reset_state)."""
+        self.set_world_state(init, num_agents, snapshot_only=True)
 
     def reset(self, world_mask=None):
         m = None
@@ -197,7 +204,11 @@ class VecCollisionAvoidanceEnv(object):
     def _ptr(t):
         return None if t is None else C.c_void_p(t.data_ptr())
 
-    def set_world_state(self, init, num_agents):
+    def set_reset_state(self, init, num_agents):
+        """New scenarios that worlds pick up at their next reset / auto-reset (ca_set_reset_state)."""
+        self.set_world_state(init, num_agents, snapshot_only=True)
+
+    def set_world_state(self, init, num_agents, snapshot_only=False):
         torch = self.torch
         init = torch.as_tensor(init, dtype=torch.float64).to(self.device).contiguous()
         nag = torch.as_tensor(num_agents, dtype=torch.int32).to(self.device).contiguous()
@@ -207,19 +218,30 @@ class VecCollisionAvoidanceEnv(object):
             raise ValueError("num_agents must have shape (%d,)" % self.W)
         if int(nag.min()) < 1 or int(nag.max()) > self.A:
             raise ValueError("num_agents must be within 1..%d" % self.A)
-        self.handle.set_world_state(self._ptr(init), self._ptr(nag), True, self._stream())
-        self.num_agents = nag
+        self.handle.set_world_state(self._ptr(init), self._ptr(nag), True, self._stream(), snapshot_only=snapshot_only)
+        if not snapshot_only:
+            self.num_agents = nag
         torch.cuda.current_stream(self.device).synchronize()  # init/nag temporaries may be freed after return
 
-    def reset(self, world_mask=None):
+    def _check_out_obs(self, out_obs):
+        if out_obs is None:
+            return self.obs
+        if (tuple(out_obs.shape) != (self.W, self.A, self.L) or out_obs.dtype != self.torch.float32
+                or not out_obs.is_cuda or not out_obs.is_contiguous()):
+            raise ValueError("out_obs must be a contiguous float32 CUDA tensor of shape (%d, %d, %d)" % (self.W, self.A, self.L))
+        return out_obs
+
+    def reset(self, world_mask=None, out_obs=None):
+        """out_obs: optional destination for the observation (e.g. a slot of a rollout's observation ring)."""
+        obs = self._check_out_obs(out_obs)
         m = None
         if world_mask is not None:
             m = self.torch.as_tensor(world_mask, dtype=self.torch.uint8).to(self.device).contiguous()
-        check(lib().ca_reset(self.handle._h, self._ptr(m), self._ptr(self.obs), self._ptr(self.sorted_idx),
+        check(lib().ca_reset(self.handle._h, self._ptr(m), self._ptr(obs), self._ptr(self.sorted_idx),
                              self._stream()), "ca_reset")
-        return self.obs
+        return obs
 
-    def step(self, actions, cont_actions=None):
+    def step(self, actions, cont_actions=None, out_obs=None):
         torch = self.torch
         if actions.dtype != torch.int32 or not actions.is_cuda or not actions.is_contiguous():
             actions = actions.to(device=self.device, dtype=torch.int32).contiguous()
@@ -227,10 +249,11 @@ class VecCollisionAvoidanceEnv(object):
             raise ValueError("actions must have shape (%d, %d)" % (self.W, self.A))
         if cont_actions is not None:
             cont_actions = cont_actions.to(device=self.device, dtype=torch.float64).contiguous()
-        check(lib().ca_step(self.handle._h, self._ptr(actions), self._ptr(cont_actions), self._ptr(self.obs),
+        obs = self._check_out_obs(out_obs)
+        check(lib().ca_step(self.handle._h, self._ptr(actions), self._ptr(cont_actions), self._ptr(obs),
                             self._ptr(self.reward), self._ptr(self.done), self._ptr(self.game_over),
                             self._ptr(self.sorted_idx), self._stream()), "ca_step")
-        return self.obs, self.reward, self.done, self.game_over
+        return obs, self.reward, self.done, self.game_over
 
     def get_state(self):
         self.torch.cuda.current_stream(self.device).synchronize()

@@ -230,6 +230,28 @@ def test_cuda_masked_reset_matches_oracle():
     gpu.close(); cpu.close()
 
 
+def test_streamed_scenarios_with_changing_agent_counts_match_oracle():
+    """ca_set_reset_state: finished worlds come back with a NEW scenario (possibly a different agent count)."""
+    from oracle.ca_oracle import OracleEnv
+    rng = np.random.default_rng(81)
+    W, A = 301, 4
+    init, nag = _random_worlds(rng, W, A, 3.0, policies=(0, 0, 1, 2))
+    cfg = _abi.default_config(W, A, auto_reset=1)
+    gpu, cpu = _host_env(cfg), OracleEnv(cfg)
+    gpu.set_world_state(init, nag); cpu.set_world_state(init, nag)
+    gpu.reset(); cpu.reset()
+    for t in range(120):
+        if t % 15 == 5:
+            init2, nag2 = _random_worlds(rng, W, A, 3.0, policies=(0, 0, 1, 2))
+            gpu.set_reset_state(init2, nag2); cpu.set_reset_state(init2, nag2)
+        act = rng.choice([1, 2, 2, 2, 3, 6, 9], size=(W, A)).astype(np.int32)
+        gpu.step(act); cpu.step(act)
+        _compare_step(gpu, cpu, "streamed t=%d" % t)
+        if t % 20 == 19:
+            _compare_state(gpu, cpu, "streamed t=%d" % t)
+    gpu.close(); cpu.close()
+
+
 def test_library_computes_time_remaining_when_nan():
     from oracle.ca_oracle import OracleEnv
     rng = np.random.default_rng(79)
