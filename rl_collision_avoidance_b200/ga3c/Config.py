@@ -8,7 +8,7 @@ import os
 
 import numpy as np
 
-from ..config import Config as EnvConfig
+from rl_collision_avoidance_b200.config import Config as EnvConfig
 
 
 class Train(EnvConfig):

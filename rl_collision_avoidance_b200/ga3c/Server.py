@@ -14,6 +14,7 @@ import numpy as np
 
 from .Config import get_config
 from .NetworkVP_rnn import NetworkVP_rnn
+from .parallel import allreduce_gradients
 from .rollout import GpuRollout
 from ..scenarios import random_worlds
 
@@ -157,13 +158,7 @@ class Server(object):
         for p in m.net.parameters():
             p.grad = None
         costs["cost_all"].backward()
-        flat = self.torch.cat([p.grad.reshape(-1) for p in m.net.parameters()])
-        self.dist.all_reduce(flat)
-        off = 0
-        for p in m.net.parameters():
-            n = p.numel()
-            p.grad.copy_(flat[off:off + n].view_as(p))
-            off += n
+        allreduce_gradients(list(m.net.parameters()))
         m.opt.step(m.learning_rate)
         m.global_step += 1
         m.last_costs = costs
