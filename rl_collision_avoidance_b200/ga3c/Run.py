@@ -9,7 +9,8 @@ def main():
     if "RANK" in os.environ and int(os.environ.get("WORLD_SIZE", "1")) > 1:
         torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        torch.distributed.init_process_group("nccl")
+        import datetime
+        torch.distributed.init_process_group("nccl", timeout=datetime.timedelta(seconds=int(os.environ.get("GA3C_NCCL_TIMEOUT_S", "600"))))
     from .Server import Server
     out = Server().main(max_seconds=float(os.environ["GA3C_MAX_SECONDS"]) if "GA3C_MAX_SECONDS" in os.environ else None)
     print("all done.", out)

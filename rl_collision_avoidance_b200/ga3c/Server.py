@@ -172,6 +172,8 @@ class Server(object):
         cfg = self.cfg
         batch = max(cfg.GPU_TRAIN_BATCH, cfg.TRAINING_MIN_BATCH_SIZE + 1)
         torch = self.torch
+        if self.dist:
+            return self._train_pending_distributed(batch, force)
         while self._pending_rows >= batch or (force and self._pending_rows > cfg.TRAINING_MIN_BATCH_SIZE):
             x = torch.cat([p[0] for p in self._pending])
             r = torch.cat([p[1] for p in self._pending])
@@ -181,6 +183,30 @@ class Server(object):
                 self.train_model(x[:n], r[:n], a[:n], 0)
             self._pending = [(x[n:], r[n:], a[n:])] if x.shape[0] > n else []
             self._pending_rows = x.shape[0] - n
+
+    def _train_pending_distributed(self, batch, force):
+        """Every rank must take part in the same number of collectives: the number of optimiser steps is agreed on
+        from the all-gathered pending row counts; a rank with fewer rows contributes smaller (possibly empty) chunks."""
+        torch, cfg = self.torch, self.cfg
+        mine = torch.tensor([self._pending_rows], dtype=torch.int64, device="cuda")
+        counts = [torch.zeros_like(mine) for _ in range(self.world_size)]
+        self.dist.all_gather(counts, mine)
+        counts = [int(c.item()) for c in counts]
+        total = sum(counts)
+        if not (total >= batch * self.world_size or (force and total > cfg.TRAINING_MIN_BATCH_SIZE)):
+            return
+        n_chunks = max(1, -(-max(counts) // batch))
+        L1 = self.rollout.L - 1
+        if self._pending:
+            x = torch.cat([p[0] for p in self._pending]); r = torch.cat([p[1] for p in self._pending])
+            a = torch.cat([p[2] for p in self._pending])
+        else:
+            x = torch.zeros((0, L1), device="cuda"); r = torch.zeros(0, device="cuda")
+            a = torch.zeros(0, dtype=torch.int32, device="cuda")
+        for xs, rs, as_ in zip(torch.tensor_split(x, n_chunks), torch.tensor_split(r, n_chunks), torch.tensor_split(a, n_chunks)):
+            if cfg.TRAIN_MODE:
+                self.train_model(xs, rs, as_, 0)
+        self._pending, self._pending_rows = [], 0
 
     def main(self, max_steps=None, max_seconds=None, quiet=False):
         """Runs until Config.EPISODES (or max_steps / max_seconds, for tests and benchmarks)."""
@@ -221,8 +247,14 @@ class Server(object):
                 last_print = now
             if max_steps is not None and steps >= max_steps:
                 break
-            if max_seconds is not None and now - t0 >= max_seconds:
-                break
+            if max_seconds is not None and steps % refresh_every == 0:
+                stop = now - t0 >= max_seconds
+                if self.dist:  # all ranks must leave the loop in the same iteration
+                    flag = self.torch.tensor([1.0 if stop else 0.0], device="cuda")
+                    self.dist.all_reduce(flag, op=self.dist.ReduceOp.MAX)
+                    stop = bool(flag.item() > 0)
+                if stop:
+                    break
         self._train_pending(force=True)
         self.torch.cuda.synchronize()
         return {"steps": steps, "seconds": time.time() - t0, "episodes": self.stats.episode_count,
