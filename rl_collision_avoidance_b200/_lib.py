@@ -13,7 +13,7 @@ PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC_DIR = os.path.join(PKG_DIR, "csrc")
 LIB_PATH = os.path.join(PKG_DIR, "libcastep.so")
 SOURCES = ["ca_step.cu"]
-HEADERS = [os.path.join(CSRC_DIR, "ca_kernels.cuh"), os.path.join(CSRC_DIR, "ca_step_fast.cuh"), os.path.join(CSRC_DIR, "ca_ga3c.cuh"), os.path.join(PKG_DIR, "..", "include", "ca_step.h")]
+HEADERS = [os.path.join(CSRC_DIR, "ca_kernels.cuh"), os.path.join(CSRC_DIR, "ca_step_fast.cuh"), os.path.join(CSRC_DIR, "ca_step_pipe.cuh"), os.path.join(CSRC_DIR, "ca_ga3c.cuh"), os.path.join(PKG_DIR, "..", "include", "ca_step.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",  # B200 only

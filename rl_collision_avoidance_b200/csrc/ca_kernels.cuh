@@ -94,6 +94,13 @@ __device__ __forceinline__ Ego ego_frame(double px, double py, double gx, double
   return e;
 }
 
+// Programmatic dependent launch (PDL): when the kernel is launched with the programmatic-stream-serialization
+// attribute its CTAs may become resident while the previous kernel in the stream is still draining; pdl_wait()
+// blocks until that kernel has completed and its writes are visible, pdl_launch_dependents() lets the NEXT kernel's
+// CTAs start filling SMs that this grid no longer needs.  Both are no-ops for a normal launch.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 __device__ __forceinline__ double shfl_d(double v, int src) { return __shfl_sync(kFull, v, src); }
 
 // compute_time_to_impact, GCA/envs/util.py:14-104 (host pos/vel, other pos/vel, combined radius)
@@ -335,6 +342,8 @@ __global__ void __launch_bounds__(kBlock) ca_world_kernel(const __grid_constant_
   const long first_world_cta = (long)blockIdx.x * kWarps * p.wpw;
   const long w = first_world_cta + (long)warp * p.wpw + wl;
   const bool world_ok = wl < p.wpw && w < p.W;
+  pdl_wait();
+  pdl_launch_dependents();
   int n = world_ok ? p.nag[w] : 0;
   bool valid = world_ok && i < n;
   const size_t g = world_ok ? (size_t)w * A + i : 0;

@@ -10,6 +10,7 @@
 
 #include "ca_kernels.cuh"
 #include "ca_step_fast.cuh"
+#include "ca_step_pipe.cuh"
 #include "ca_ga3c.cuh"
 
 namespace {
@@ -58,6 +59,11 @@ struct ca_env {
   int tile_floats = 0;
   bool bulk_ok = true;
   bool force_generic = false;
+  int kernel_choice = 1;       // 1 = one-shot specialised kernel (default, fastest measured), 0 = pipelined persistent kernel
+  bool use_pdl = true;         // programmatic dependent launch for step kernels (CA_DISABLE_PDL=1 turns it off)
+  int pipe_min_blocks = 0;     // 0 = default instantiation
+  int pipe_grid = 0;
+  size_t smem_pipe = 0;
   size_t smem_fast = 0;        // dynamic shared memory of the specialised step kernel (observation tile only)
   double* slab = nullptr;      // 20 double arrays of W*A: live state then snapshot
   uint8_t* bytes = nullptr;    // 4 uint8 arrays of W*A: flags, policy, flags0, policy0
@@ -125,8 +131,12 @@ __global__ void pack_state_kernel(ca::StateArrays s, double* __restrict__ out, l
   r[CA_S_PREF_SPEED] = s.ps[g]; r[CA_S_FLAGS] = (double)s.flags[g]; r[CA_S_POLICY] = (double)s.policy[g];
 }
 
+// Array stride: W*A rounded up to 32 elements so that every SoA array starts 256-byte aligned (TMA bulk copies
+// need 16-byte aligned sources).
+size_t array_stride(const ca_env* e) { return (((size_t)e->W * e->A) + 31) & ~(size_t)31; }
+
 void carve(ca_env* e) {
-  const size_t n = (size_t)e->W * e->A;
+  const size_t n = array_stride(e);
   double* d = e->slab;
   ca::StateArrays* arr[2] = {&e->s, &e->s0};
   for (int k = 0; k < 2; ++k) {
@@ -171,29 +181,96 @@ bool has_fast_kernel(const ca_env* e) {
   }
 }
 
-cudaError_t set_fast_smem_attr(int A, int bytes) {
+cudaError_t set_fast_smem_attr(int A, int bytes);
+
+// Instantiations of the pipelined kernel: (agent slots, min CTAs per SM used for register allocation).
+#define CA_PIPE_VARIANTS(X) X(2, 6) X(3, 6) X(4, 5) X(4, 7) X(5, 5) X(6, 5) X(8, 4) X(10, 3)
+
+int default_pipe_min_blocks(int A) {
   switch (A) {
-#define X(n) case n: return cudaFuncSetAttribute(ca::ca_step_kernel<n>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
-    CA_FAST_SIZES(X)
-#undef X
-    default: return cudaSuccess;
+    case 2: case 3: return 6;
+    case 4: return 5;
+    case 5: case 6: return 5;
+    case 8: return 4;
+    default: return 3;
   }
+}
+
+const void* pipe_kernel_ptr(int A, int mb) {
+#define X(a, b) if (A == a && mb == b) return (const void*)ca::ca_step_pipe_kernel<a, b>;
+  CA_PIPE_VARIANTS(X)
+#undef X
+  return nullptr;
+}
+
+// One-shot specialised kernels: (agent slots, min CTAs/SM the register allocation targets).  The second number was
+// picked from -Xptxas -v (largest occupancy without heavy spilling) and, for A = 4, measured on B200:
+// 7 CTAs/SM lets 65 536 x 4 worlds (8192 warp chunks) finish in 2 rounds of 4144 resident warps instead of 3.
+#define CA_ONESHOT_VARIANTS(X) X(2, 8) X(3, 6) X(4, 5) X(4, 6) X(4, 7) X(4, 8) X(5, 5) X(6, 5) X(8, 4) X(10, 3)
+
+int default_oneshot_min_blocks(int A) {
+  switch (A) {
+    case 2: return 8;
+    case 3: return 6;
+    case 4: return 7;
+    case 5: case 6: return 5;
+    case 8: return 4;
+    default: return 3;
+  }
+}
+
+const void* fast_kernel_ptr(int A) {
+  int mb = default_oneshot_min_blocks(A);
+  const char* env = getenv("CA_ONESHOT_MINBLOCKS");
+  const int v = env ? atoi(env) : 0;
+#define X(a, b) if (A == a && v == b) mb = v;
+  CA_ONESHOT_VARIANTS(X)
+#undef X
+#define X(a, b) if (A == a && mb == b) return (const void*)ca::ca_step_kernel<a, b>;
+  CA_ONESHOT_VARIANTS(X)
+#undef X
+  return nullptr;
+}
+
+// Launch with the programmatic-stream-serialization attribute (PDL): back-to-back steps overlap the launch latency
+// and ramp-up of step t+1 with the tail of step t; the kernels call griddepcontrol.wait before touching global data.
+cudaError_t set_fast_smem_attr(int A, int bytes) {
+  const void* fn = fast_kernel_ptr(A);
+  return fn ? cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes) : cudaSuccess;
+}
+
+int launch_pdl(const void* fn, int grid, size_t smem, cudaStream_t st, ca::Params& p, bool pdl) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(kBlock);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl ? 1 : 0;
+  void* args[] = {&p};
+  CA_CUDA(cudaLaunchKernelExC(&cfg, fn, args));
+  return CA_OK;
 }
 
 int launch_world_kernel(ca_env* e, bool step, ca::Params& p, cudaStream_t st) {
   p.use_bulk_store = (e->bulk_ok && aligned16(p.obs) && (e->tile_floats % 4) == 0) ? 1 : 0;
   p.warp_store = ((e->tile_floats / kWarps) % 4) == 0 ? 1 : 0;
-  if (step && has_fast_kernel(e)) {
-    switch (e->A) {
-#define X(n) case n: ca::ca_step_kernel<n><<<e->grid, kBlock, e->smem_fast, st>>>(p); break;
-      CA_FAST_SIZES(X)
-#undef X
-    }
+  int rc;
+  if (step && has_fast_kernel(e) && e->kernel_choice == 0) {
+    p.use_bulk_store = (e->bulk_ok && aligned16(p.obs)) ? 1 : 0;  // per-warp tile; its own size check is in-kernel
+    rc = launch_pdl(pipe_kernel_ptr(e->A, e->pipe_min_blocks), e->pipe_grid, e->smem_pipe, st, p, e->use_pdl);
+  } else if (step && has_fast_kernel(e)) {
+    rc = launch_pdl(fast_kernel_ptr(e->A), e->grid, e->smem_fast, st, p, e->use_pdl);
   } else if (step) {
-    ca::ca_world_kernel<true><<<e->grid, kBlock, e->smem_bytes, st>>>(p);
+    rc = launch_pdl((const void*)ca::ca_world_kernel<true>, e->grid, e->smem_bytes, st, p, e->use_pdl);
   } else {
-    ca::ca_world_kernel<false><<<e->grid, kBlock, e->smem_bytes, st>>>(p);
+    rc = launch_pdl((const void*)ca::ca_world_kernel<false>, e->grid, e->smem_bytes, st, p, false);
   }
+  if (rc != CA_OK) return rc;
   CA_CUDA(cudaPeekAtLastError());
   e->launches += 1;
   return CA_OK;
@@ -312,12 +389,37 @@ int ca_create(const ca_config* cfg, ca_env** out) {
   if (ce == cudaSuccess)
     ce = cudaFuncSetAttribute(ca::ca_world_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem_bytes);
   if (ce == cudaSuccess) ce = set_fast_smem_attr(e->A, (int)e->smem_fast);
+  const char* kc = getenv("CA_STEP_KERNEL");  // "oneshot" (default) | "pipe" | "generic"
+  if (kc && strcmp(kc, "oneshot") == 0) e->kernel_choice = 1;
+  if (kc && strcmp(kc, "pipe") == 0) e->kernel_choice = 0;
+  const char* np = getenv("CA_DISABLE_PDL");
+  e->use_pdl = !(np && np[0] == '1');
+  if (kc && strcmp(kc, "generic") == 0) e->force_generic = true;
+  if (ce == cudaSuccess && has_fast_kernel(e)) {
+    e->pipe_min_blocks = default_pipe_min_blocks(e->A);
+    const char* mb = getenv("CA_PIPE_MINBLOCKS");
+    if (mb && pipe_kernel_ptr(e->A, atoi(mb))) e->pipe_min_blocks = atoi(mb);
+    const void* fn = pipe_kernel_ptr(e->A, e->pipe_min_blocks);
+    const int warp_tile_bytes = ((e->tile_floats / kWarps) * 4 + 15) / 16 * 16;
+    e->smem_pipe = (size_t)kWarps * (ca::kStageBytes + warp_tile_bytes + 16);
+    ce = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem_pipe);
+    int per_sm = 0, sms = 0;
+    if (ce == cudaSuccess) ce = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, kBlock, e->smem_pipe);
+    if (ce == cudaSuccess) ce = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, cfg->device);
+    if (ce == cudaSuccess) {
+      const char* pg = getenv("CA_PIPE_CTAS_PER_SM");
+      if (pg && atoi(pg) > 0 && atoi(pg) < per_sm) per_sm = atoi(pg);
+      const int resident = sms * (per_sm > 0 ? per_sm : 1);
+      e->pipe_grid = e->grid < resident ? e->grid : resident;
+    }
+  }
   if (ce != cudaSuccess) {
     delete e;
     return fail(CA_ERR_CUDA, "kernel image not usable on this device (built for sm_100a): %s", cudaGetErrorString(ce));
   }
   const size_t n = (size_t)e->W * e->A;
-  if (cudaMalloc(&e->slab, n * 20 * sizeof(double)) != cudaSuccess || cudaMalloc(&e->bytes, n * 4) != cudaSuccess ||
+  const size_t ns = array_stride(e);
+  if (cudaMalloc(&e->slab, ns * 20 * sizeof(double)) != cudaSuccess || cudaMalloc(&e->bytes, ns * 4) != cudaSuccess ||
       cudaMalloc(&e->nag, (size_t)e->W * 2 * sizeof(int32_t)) != cudaSuccess) {
     cudaFree(e->slab); cudaFree(e->bytes); cudaFree(e->nag);
     delete e;

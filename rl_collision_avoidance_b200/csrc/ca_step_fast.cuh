@@ -162,8 +162,8 @@ __device__ __forceinline__ void fast_store_warp_tile(const Params& p, const floa
   for (int q = lane; q < nfloats; q += 32) dst[q] = wtile[q];
 }
 
-template <int kA>
-__global__ void __launch_bounds__(kBlock) ca_step_kernel(const __grid_constant__ Params p) {
+template <int kA, int kMinBlocks = 1>
+__global__ void __launch_bounds__(kBlock, kMinBlocks) ca_step_kernel(const __grid_constant__ Params p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   constexpr int wpw = 32 / kA;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -173,9 +173,11 @@ __global__ void __launch_bounds__(kBlock) ca_step_kernel(const __grid_constant__
   const long first_world_warp = ((long)blockIdx.x * kWarps + warp) * wpw;
   const long w = first_world_warp + wl;
   const bool world_ok = wl < wpw && w < p.W;
+  const size_t g = world_ok ? (size_t)w * kA + i : 0;
+  pdl_wait();                // nothing produced by the previous kernel is read above this line
+  pdl_launch_dependents();
   int n = world_ok ? p.nag[w] : 0;
   bool valid = world_ok && i < n;
-  const size_t g = world_ok ? (size_t)w * kA + i : 0;
   const unsigned gmask = (kA >= 32 ? kFull : ((1u << kA) - 1u)) << (base & 31);
 
   // per-warp tile: rows of the warp's wpw worlds; warp tiles are laid out back to back (no padding) so the
@@ -184,10 +186,15 @@ __global__ void __launch_bounds__(kBlock) ca_step_kernel(const __grid_constant__
   float* row = wtile + ((size_t)wl * kA + i) * p.L;
   int32_t* sidx_row = (p.sidx && world_ok) ? p.sidx + g * p.M : nullptr;
 
+  // The state loads do not wait for the agent count: every slot of an existing world is loaded (absent slots hold
+  // zeros / stale values and are discarded below), so only ONE DRAM round trip is exposed instead of two.
   Agent a;
-  if (valid) load_agent(p.s, g, a); else zero_agent(a);
   int act = 0;
-  if (valid) act = p.actions[g];
+  if (world_ok) {
+    load_agent(p.s, g, a);
+    act = p.actions[g];
+  }
+  if (!valid) { zero_agent(a); act = 0; }
 
   // ---- _take_action (:217-252)
   const bool was_done = (a.flags & CA_F_DONE_MASK) != 0;

@@ -295,27 +295,33 @@ def test_bulk_store_and_plain_store_paths_agree(monkeypatch):
                                       (5, 2, "closest_last"), (6, 5, "closest_first"), (8, 3, "closest_first"),
                                       (10, 9, "closest_last")])
 def test_specialised_and_generic_kernels_agree_bitwise(monkeypatch, A, M, sort):
-    """ca_step_kernel<A> (unrolled, register keys) and the generic ca_world_kernel<true> are the same arithmetic."""
+    """ca_step_kernel<A> (one-shot, unrolled, register keys), ca_step_pipe_kernel<A> (persistent, TMA-prefetched state,
+    int keys) and the generic ca_world_kernel<true> are the same arithmetic; PDL launches change nothing."""
     rng = np.random.default_rng(90 + A)
     W = 777
     init, nag = _random_worlds(rng, W, A, 3.0 + 0.3 * A, policies=(0, 0, 0, 1, 2))
+    init2, nag2 = _random_worlds(rng, W, A, 3.0 + 0.3 * A, policies=(0, 0, 0, 1, 2))
     acts = rng.choice([0, 1, 2, 2, 2, 3, 4, 6, 9], size=(40, W, A)).astype(np.int32)
     outs = []
-    for force in ("0", "1"):
-        monkeypatch.setenv("CA_FORCE_GENERIC", force)
+    for kern, pdl_off in (("generic", "1"), ("oneshot", "0"), ("pipe", "0"), ("oneshot", "1")):
+        monkeypatch.setenv("CA_STEP_KERNEL", kern)
+        monkeypatch.setenv("CA_DISABLE_PDL", pdl_off)
         env = _host_env(_abi.default_config(W, A, M, sort_method=_abi.SORT_METHODS[sort], auto_reset=1))
         env.set_world_state(init, nag)
         env.reset()
         rec = []
         for t in range(40):
+            if t == 10:
+                env.set_reset_state(init2, nag2)   # streamed scenarios with other agent counts
             env.step(acts[t])
             rec.append((env.obs.copy(), env.reward.copy(), env.done.copy(), env.game_over.copy(), env.sorted_idx.copy()))
         outs.append((rec, env.get_state()))
         env.close()
-    for t in range(40):
-        for x, y in zip(outs[0][0][t], outs[1][0][t]):
-            np.testing.assert_array_equal(x, y)
-    np.testing.assert_array_equal(outs[0][1], outs[1][1])
+    for other in outs[1:]:
+        for t in range(40):
+            for x, y in zip(outs[0][0][t], other[0][t]):
+                np.testing.assert_array_equal(x, y)
+        np.testing.assert_array_equal(outs[0][1], other[1])
 
 
 # ----------------------------------------------------------------------------- full-size properties
