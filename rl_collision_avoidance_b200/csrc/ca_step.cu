@@ -9,8 +9,8 @@
 #include <string>
 
 #include "ca_kernels.cuh"
-#include "ca_step_fast.cuh"
 #include "ca_step_pipe.cuh"
+#include "ca_step_fast.cuh"
 #include "ca_ga3c.cuh"
 
 namespace {
@@ -60,6 +60,7 @@ struct ca_env {
   bool bulk_ok = true;
   bool force_generic = false;
   int kernel_choice = 1;       // 1 = one-shot specialised kernel (default, fastest measured), 0 = pipelined persistent kernel
+  bool store_vec4 = false;     // CA_STORE_MODE=vec4: 128-bit copy-out instead of the TMA bulk store (one-shot kernel)
   bool use_pdl = true;         // programmatic dependent launch for step kernels (CA_DISABLE_PDL=1 turns it off)
   int pipe_min_blocks = 0;     // 0 = default instantiation
   int pipe_grid = 0;
@@ -206,16 +207,15 @@ const void* pipe_kernel_ptr(int A, int mb) {
 // One-shot specialised kernels: (agent slots, min CTAs/SM the register allocation targets).  The second number was
 // picked from -Xptxas -v (largest occupancy without heavy spilling) and, for A = 4, measured on B200:
 // 7 CTAs/SM lets 65 536 x 4 worlds (8192 warp chunks) finish in 2 rounds of 4144 resident warps instead of 3.
-#define CA_ONESHOT_VARIANTS(X) X(2, 8) X(3, 6) X(4, 5) X(4, 6) X(4, 7) X(4, 8) X(5, 5) X(6, 5) X(8, 4) X(10, 3)
+#define CA_ONESHOT_VARIANTS(X) X(2, 8) X(3, 8) X(4, 6) X(4, 7) X(4, 8) X(5, 6) X(6, 6) X(8, 4) X(8, 5) X(10, 3) X(10, 4)
 
 int default_oneshot_min_blocks(int A) {
   switch (A) {
-    case 2: return 8;
-    case 3: return 6;
+    case 2: case 3: return 8;
     case 4: return 7;
-    case 5: case 6: return 5;
-    case 8: return 4;
-    default: return 3;
+    case 5: case 6: return 6;
+    case 8: return 5;
+    default: return 4;
   }
 }
 
@@ -264,6 +264,7 @@ int launch_world_kernel(ca_env* e, bool step, ca::Params& p, cudaStream_t st) {
     p.use_bulk_store = (e->bulk_ok && aligned16(p.obs)) ? 1 : 0;  // per-warp tile; its own size check is in-kernel
     rc = launch_pdl(pipe_kernel_ptr(e->A, e->pipe_min_blocks), e->pipe_grid, e->smem_pipe, st, p, e->use_pdl);
   } else if (step && has_fast_kernel(e)) {
+    if (e->store_vec4 && aligned16(p.obs) && p.warp_store) p.use_bulk_store = 2;
     rc = launch_pdl(fast_kernel_ptr(e->A), e->grid, e->smem_fast, st, p, e->use_pdl);
   } else if (step) {
     rc = launch_pdl((const void*)ca::ca_world_kernel<true>, e->grid, e->smem_bytes, st, p, e->use_pdl);
@@ -392,6 +393,8 @@ int ca_create(const ca_config* cfg, ca_env** out) {
   const char* kc = getenv("CA_STEP_KERNEL");  // "oneshot" (default) | "pipe" | "generic"
   if (kc && strcmp(kc, "oneshot") == 0) e->kernel_choice = 1;
   if (kc && strcmp(kc, "pipe") == 0) e->kernel_choice = 0;
+  const char* sm = getenv("CA_STORE_MODE");
+  e->store_vec4 = sm && strcmp(sm, "vec4") == 0;
   const char* np = getenv("CA_DISABLE_PDL");
   e->use_pdl = !(np && np[0] == '1');
   if (kc && strcmp(kc, "generic") == 0) e->force_generic = true;

@@ -8,6 +8,7 @@
 // reset, and agent counts without an instantiation run on the generic kernel.
 #pragma once
 #include "ca_kernels.cuh"
+#include "ca_step_pipe.cuh"
 
 namespace ca {
 
@@ -146,7 +147,7 @@ __device__ __forceinline__ void fast_store_warp_tile(const Params& p, const floa
   const int nw = worlds_left < wpw ? (int)worlds_left : wpw;
   const int nfloats = nw * kA * p.L;
   float* dst = p.obs + (size_t)first_world_warp * kA * p.L;
-  if (p.use_bulk_store && nw == wpw) {
+  if (p.use_bulk_store == 1 && nw == wpw) {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncwarp();
     if (lane == 0) {
@@ -159,6 +160,12 @@ __device__ __forceinline__ void fast_store_warp_tile(const Params& p, const floa
     return;
   }
   __syncwarp();
+  if (p.use_bulk_store == 2 && (nfloats & 3) == 0) {  // 128-bit coalesced copy-out, no wait on the async proxy
+    const float4* s4 = reinterpret_cast<const float4*>(wtile);
+    float4* d4 = reinterpret_cast<float4*>(dst);
+    for (int q = lane; q < nfloats / 4; q += 32) d4[q] = s4[q];
+    return;
+  }
   for (int q = lane; q < nfloats; q += 32) dst[q] = wtile[q];
 }
 
@@ -243,10 +250,10 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks) ca_step_kernel(const __gri
   }
 
   Ego e = ego_frame(a.px, a.py, a.gx, a.gy, a.hd);
-  Others<kA> o;
+  OthersLite<kA> o;
   bool coll;
   double nearest;
-  fast_pair_pass<kA, true>(p, a, e, valid, n, i, base, o, coll, nearest);
+  pipe_pair_pass<kA, true>(p, a, e, valid, n, i, base, o, coll, nearest);
 
   // ---- _compute_rewards (:319-368)
   double r = p.r_step;
@@ -283,7 +290,7 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks) ca_step_kernel(const __gri
   const bool do_reset = world_ok && over && p.auto_reset;
 
   if (!__any_sync(kFull, do_reset)) {
-    fast_write_obs_row<kA>(p, a, e, world_ok, valid, i, base, o, row, sidx_row);
+    pipe_write_obs_row<kA>(p, a, e, world_ok, valid, i, base, o, row, sidx_row);
   } else {
     // DummyVecEnv semantics: worlds that finished reload their injected initial state and observe again;
     // the other worlds of the warp observe their post-step state.
@@ -296,8 +303,8 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks) ca_step_kernel(const __gri
     }
     bool c_unused;
     double n_unused;
-    fast_pair_pass<kA, false>(p, a, e, valid, n, i, base, o, c_unused, n_unused);
-    fast_write_obs_row<kA>(p, a, e, world_ok, valid, i, base, o, row, sidx_row);
+    pipe_pair_pass<kA, false>(p, a, e, valid, n, i, base, o, c_unused, n_unused);
+    pipe_write_obs_row<kA>(p, a, e, world_ok, valid, i, base, o, row, sidx_row);
   }
 
   // ---- state write-back
