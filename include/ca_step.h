@@ -154,6 +154,27 @@ int ca_set_world_state(ca_env* env, const double* init, const int32_t* num_agent
  * scenarios are streamed in (≙ test_case_fn being called again on every env.reset(), collision_avoidance_env.py:283). */
 int ca_set_reset_state(ca_env* env, const double* init, const int32_t* num_agents, int on_device, void* stream);
 
+/* On-device scenario generator (≙ get_testcase_random + cadrl_test_case_to_agents, GCA/envs/test_cases.py:95-118,263-326,
+ * and generate_rand_test_case_multi, GCA/envs/policies/CADRL/scripts/multi/gen_rand_testcases.py:104-437): writes fresh
+ * random test cases into the reset snapshot.  Distributional parity with the reference (Philox instead of MT19937). */
+typedef struct ca_scenario_config {
+  int32_t min_agents, max_agents;       /* num_agents ~ U{min..max} (reference: 2..MAX_NUM_AGENTS_IN_ENVIRONMENT) */
+  int32_t side_split_agents;            /* worlds with fewer agents use the small side range (config.py:57-60: 5) */
+  int32_t ensure_learner;               /* policy_to_ensure = 'learning_ga3c' (config.py:51) */
+  double side_small_lo, side_small_hi;  /* [4, 5] */
+  double side_large_lo, side_large_hi;  /* [6, 8] */
+  double p_swap, p_circle;              /* 0.15, 0.15 (gen_rand_testcases.py:123-133); the rest are random cases */
+  double speed_lo, speed_hi;            /* speed_bnds [0.5, 2.0]; pref_speed = max of two draws */
+  double radius_lo, radius_hi;          /* radius_bnds [0.2, 0.8] */
+  double p_noncoop, p_learning;         /* policy_distr [0.05, 0.9, 0.05] over noncoop / learning_ga3c / static */
+} ca_scenario_config;
+
+int ca_default_scenario_config(ca_scenario_config* cfg, int32_t max_agents);
+
+/* Fill the reset snapshot of every world (only_consumed == 0) or of the worlds that have reset since the last call
+ * (only_consumed != 0) with new scenarios.  Stream ordered; call ca_reset afterwards to start all worlds from them. */
+int ca_generate_scenarios(ca_env* env, const ca_scenario_config* cfg, uint64_t seed, int only_consumed, void* stream);
+
 /* Reset worlds to their injected initial state (world_mask: device uint8[W], NULL = all) and write the
  * first observation of every world (unmasked worlds: their current observation) to obs (device float[W][A][L]);
  * sorted_idx (device int32[W][A][M], may be NULL) receives the neighbour order (-1 = empty slot). */

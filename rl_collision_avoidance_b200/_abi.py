@@ -75,6 +75,14 @@ class CaGa3cBuffers(C.Structure):
     ]
 
 
+class CaScenarioConfig(C.Structure):
+    _fields_ = [("min_agents", C.c_int32), ("max_agents", C.c_int32), ("side_split_agents", C.c_int32),
+                ("ensure_learner", C.c_int32)] + \
+               [(n, C.c_double) for n in ("side_small_lo", "side_small_hi", "side_large_lo", "side_large_hi", "p_swap",
+                                          "p_circle", "speed_lo", "speed_hi", "radius_lo", "radius_hi", "p_noncoop",
+                                          "p_learning")]
+
+
 def default_config(num_worlds, max_agents, max_others_observed=None, **overrides):
     """Reference defaults, GCA/envs/config.py:30-47,64-76,171 and collision_avoidance_env.py:76,463-483."""
     cfg = CaConfig()

@@ -13,7 +13,7 @@ PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC_DIR = os.path.join(PKG_DIR, "csrc")
 LIB_PATH = os.path.join(PKG_DIR, "libcastep.so")
 SOURCES = ["ca_step.cu"]
-HEADERS = [os.path.join(CSRC_DIR, "ca_kernels.cuh"), os.path.join(CSRC_DIR, "ca_step_fast.cuh"), os.path.join(CSRC_DIR, "ca_step_pipe.cuh"), os.path.join(CSRC_DIR, "ca_ga3c.cuh"), os.path.join(PKG_DIR, "..", "include", "ca_step.h")]
+HEADERS = [os.path.join(CSRC_DIR, "ca_kernels.cuh"), os.path.join(CSRC_DIR, "ca_step_fast.cuh"), os.path.join(CSRC_DIR, "ca_step_pipe.cuh"), os.path.join(CSRC_DIR, "ca_ga3c.cuh"), os.path.join(CSRC_DIR, "ca_scenarios.cuh"), os.path.join(PKG_DIR, "..", "include", "ca_step.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",  # B200 only
@@ -26,7 +26,7 @@ NVCC_FLAGS = [
 EXPORTS = [
     "ca_default_config", "ca_create", "ca_destroy", "ca_set_world_state", "ca_set_reset_state", "ca_reset", "ca_step", "ca_step_host",
     "ca_reset_host", "ca_get_state", "ca_launch_count", "ca_host_alloc", "ca_host_free", "ca_nstep_returns",
-    "ca_ga3c_record", "ca_ga3c_episode_stats",
+    "ca_ga3c_record", "ca_ga3c_episode_stats", "ca_default_scenario_config", "ca_generate_scenarios",
     "ca_strerror", "ca_last_error", "ca_abi_version",
 ]
 
@@ -92,6 +92,8 @@ def lib():
     L.ca_ga3c_record.argtypes = [C.POINTER(_abi.CaGa3cBuffers), i64, i32, i32, i32, i32, i32, C.c_float, vp, vp, vp, vp, vp,
                                  C.c_int, vp]
     L.ca_ga3c_episode_stats.argtypes = [vp, vp, vp, vp, vp, vp, i32, i32, i32, C.c_int, vp]
+    L.ca_default_scenario_config.argtypes = [C.POINTER(_abi.CaScenarioConfig), i32]
+    L.ca_generate_scenarios.argtypes = [vp, C.POINTER(_abi.CaScenarioConfig), C.c_uint64, C.c_int, vp]
     L.ca_strerror.argtypes = [C.c_int]
     L.ca_strerror.restype = C.c_char_p
     L.ca_last_error.restype = C.c_char_p

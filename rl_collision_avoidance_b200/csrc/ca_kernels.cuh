@@ -44,6 +44,7 @@ struct Params {
   StateArrays s0;       // snapshot injected by ca_set_world_state (for reset)
   int32_t* nag;         // [W] live agent count per world
   const int32_t* nag0;  // [W] agent count of the reset snapshot (a world may come back with a different count)
+  uint8_t* consumed;    // [W] set to 1 when a world takes its snapshot (the scenario generator refills those)
   // I/O (device)
   const int32_t* actions;  // [W*A]
   const double* cont;      // [W*A*2] or null
@@ -459,7 +460,7 @@ __global__ void __launch_bounds__(kBlock) ca_world_kernel(const __grid_constant_
     if (do_reset) {
       n = p.nag0[w];
       valid = i < n;
-      if (i == 0) p.nag[w] = n;
+      if (i == 0) { p.nag[w] = n; p.consumed[w] = 1; }
       if (valid) load_agent(p.s0, g, a); else zero_agent(a);
       e = ego_frame(a.px, a.py, a.gx, a.gy, a.hd);
     }

@@ -12,6 +12,7 @@
 #include "ca_step_pipe.cuh"
 #include "ca_step_fast.cuh"
 #include "ca_ga3c.cuh"
+#include "ca_scenarios.cuh"
 
 namespace {
 
@@ -69,6 +70,8 @@ struct ca_env {
   double* slab = nullptr;      // 20 double arrays of W*A: live state then snapshot
   uint8_t* bytes = nullptr;    // 4 uint8 arrays of W*A: flags, policy, flags0, policy0
   int32_t* nag = nullptr;      // [2][W]: live agent counts, then the snapshot's
+  uint8_t* consumed = nullptr; // [W]: world took its snapshot since the last ca_generate_scenarios
+  uint64_t gen_calls = 0;
   ca::StateArrays s{}, s0{};
   bool initialised = false;
   int64_t launches = 0;
@@ -162,7 +165,7 @@ ca::Params make_params(const ca_env* e) {
   p.r_min = c.min_possible_reward; p.r_max = c.max_possible_reward;
   p.max_heading_change = c.max_heading_change;
   p.sensing_horizon = c.sensing_horizon;
-  p.s = e->s; p.s0 = e->s0; p.nag = e->nag; p.nag0 = e->nag + e->W;
+  p.s = e->s; p.s0 = e->s0; p.nag = e->nag; p.nag0 = e->nag + e->W; p.consumed = e->consumed;
   return p;
 }
 
@@ -423,13 +426,15 @@ int ca_create(const ca_config* cfg, ca_env** out) {
   const size_t n = (size_t)e->W * e->A;
   const size_t ns = array_stride(e);
   if (cudaMalloc(&e->slab, ns * 20 * sizeof(double)) != cudaSuccess || cudaMalloc(&e->bytes, ns * 4) != cudaSuccess ||
-      cudaMalloc(&e->nag, (size_t)e->W * 2 * sizeof(int32_t)) != cudaSuccess) {
-    cudaFree(e->slab); cudaFree(e->bytes); cudaFree(e->nag);
+      cudaMalloc(&e->nag, (size_t)e->W * 2 * sizeof(int32_t)) != cudaSuccess ||
+      cudaMalloc(&e->consumed, (size_t)e->W) != cudaSuccess) {
+    cudaFree(e->slab); cudaFree(e->bytes); cudaFree(e->nag); cudaFree(e->consumed);
     delete e;
     cudaGetLastError();
     return fail(CA_ERR_ALLOC, "cudaMalloc of %zu state bytes failed", n * 20 * sizeof(double));
   }
   carve(e);
+  cudaMemset(e->consumed, 0, (size_t)e->W);
   *out = e;
   return CA_OK;
 }
@@ -438,7 +443,7 @@ int ca_destroy(ca_env* e) {
   if (!e) return CA_OK;
   DeviceGuard guard(e->cfg.device);
   cudaDeviceSynchronize();
-  cudaFree(e->slab); cudaFree(e->bytes); cudaFree(e->nag);
+  cudaFree(e->slab); cudaFree(e->bytes); cudaFree(e->nag); cudaFree(e->consumed);
   cudaFree(e->d_actions); cudaFree(e->d_cont); cudaFree(e->d_obs); cudaFree(e->d_reward);
   cudaFree(e->d_done); cudaFree(e->d_over); cudaFree(e->d_mask); cudaFree(e->d_sidx);
   if (e->hstream) cudaStreamDestroy(e->hstream);
@@ -601,6 +606,50 @@ int ca_nstep_returns(const float* reward, const float* bootstrap, float* out, in
   ca::nstep_returns_kernel<<<(N + threads - 1) / threads, threads, 0, (cudaStream_t)stream>>>(reward, bootstrap, out, T,
                                                                                               N, gamma);
   CA_CUDA(cudaPeekAtLastError());
+  return CA_OK;
+}
+
+int ca_default_scenario_config(ca_scenario_config* c, int32_t max_agents) {
+  if (!c || max_agents < 1 || max_agents > CA_MAX_AGENTS) return fail(CA_ERR_INVALID_ARG, "bad argument");
+  memset(c, 0, sizeof(*c));
+  c->min_agents = max_agents >= 2 ? 2 : 1;  // np.random.randint(2, MAX_NUM_AGENTS_IN_ENVIRONMENT + 1), test_cases.py:97
+  c->max_agents = max_agents;
+  c->side_split_agents = 5;                 // config.py:57-60
+  c->ensure_learner = 1;                    // config.py:51
+  c->side_small_lo = 4; c->side_small_hi = 5; c->side_large_lo = 6; c->side_large_hi = 8;
+  c->p_swap = 0.15; c->p_circle = 0.15;     // gen_rand_testcases.py:123-133
+  c->speed_lo = 0.5; c->speed_hi = 2.0; c->radius_lo = 0.2; c->radius_hi = 0.8;  // config.py:55-56
+  c->p_noncoop = 0.05; c->p_learning = 0.9; // config.py:52-54
+  return CA_OK;
+}
+
+int ca_generate_scenarios(ca_env* e, const ca_scenario_config* c, uint64_t seed, int only_consumed, void* stream) {
+  if (!e || !c) return fail(CA_ERR_INVALID_ARG, "NULL argument");
+  if (c->min_agents < 1 || c->max_agents > e->A || c->min_agents > c->max_agents)
+    return fail(CA_ERR_INVALID_ARG, "agent count range %d..%d outside 1..%d", c->min_agents, c->max_agents, e->A);
+  if (!(c->speed_lo > 0) || c->speed_hi < c->speed_lo || !(c->radius_lo > 0) || c->radius_hi < c->radius_lo ||
+      !(c->side_small_lo > 0) || !(c->side_large_lo > 0) || c->p_swap < 0 || c->p_circle < 0 || c->p_swap + c->p_circle > 1 ||
+      c->p_noncoop < 0 || c->p_learning < 0 || c->p_noncoop + c->p_learning > 1.0 + 1e-12)
+    return fail(CA_ERR_INVALID_ARG, "bad scenario distribution parameters");
+  DeviceGuard guard(e->cfg.device);
+  ca::ScenarioParams p;
+  memset(&p, 0, sizeof(p));
+  p.c = *c; p.s0 = e->s0; p.nag0 = e->nag + e->W; p.consumed = e->consumed; p.W = e->W; p.A = e->A;
+  p.only_consumed = only_consumed; p.dt = e->cfg.dt; p.thr = e->cfg.near_goal_threshold;
+  p.max_time_ratio = e->cfg.max_time_ratio; p.seed = seed; p.offset = e->gen_calls * 4096ull;
+  e->gen_calls += 1;
+  const int threads = 128;
+  ca::generate_scenarios_kernel<<<(e->W + threads - 1) / threads, threads, 0, (cudaStream_t)stream>>>(p);
+  CA_CUDA(cudaPeekAtLastError());
+  e->launches += 1;
+  if (!e->initialised && !only_consumed) {
+    // first use without ca_set_world_state: the generated snapshot defines the worlds; the caller must ca_reset (all
+    // worlds) before stepping.  Live worlds of an initialised handle are never touched by the generator.
+    CA_CUDA(cudaMemcpyAsync(e->nag, e->nag + e->W, (size_t)e->W * sizeof(int32_t), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    CA_CUDA(cudaMemsetAsync(e->slab, 0, array_stride(e) * 10 * sizeof(double), (cudaStream_t)stream));
+    CA_CUDA(cudaMemsetAsync(e->bytes, 0, array_stride(e) * 2, (cudaStream_t)stream));
+    e->initialised = true;
+  }
   return CA_OK;
 }
 

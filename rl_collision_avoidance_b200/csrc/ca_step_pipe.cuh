@@ -351,7 +351,7 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks) ca_step_pipe_kernel(const 
       if (do_reset) {
         n = p.nag0[w];
         valid = i < n;
-        if (i == 0) p.nag[w] = n;
+        if (i == 0) { p.nag[w] = n; p.consumed[w] = 1; }
         if (valid) load_agent(p.s0, g, a); else zero_agent(a);
         e = ego_frame(a.px, a.py, a.gx, a.gy, a.hd);
       }

@@ -118,6 +118,11 @@ class Server(object):
         self.rng = np.random.default_rng(seed)
         init, nag = self._new_scenarios()
         self.rollout = GpuRollout(cfg, self.model, self.num_worlds, init, nag, device=self.device_index, seed=seed)
+        # from here on scenarios come from the on-device generator: every world that finishes an episode is handed a
+        # fresh test case for its next one (≙ test_case_fn(**TEST_CASE_ARGS) on each env.reset())
+        self._scenario_cfg = self.rollout.env.scenario_config(cfg.TEST_CASE_ARGS)
+        self._scenario_seed = int(seed) * 7919 + 17
+        self.rollout.env.generate_scenarios(self._scenario_cfg, self._scenario_seed, only_consumed=False)
         self._pending = []
         self._pending_rows = 0
 
@@ -227,10 +232,8 @@ class Server(object):
                 self._pending.append((x.clone(), r.clone(), a.clone()))
                 self._pending_rows += int(x.shape[0])
             self._train_pending()
+            self.rollout.env.generate_scenarios(self._scenario_cfg, self._scenario_seed, only_consumed=True)
             if steps % refresh_every == 0:
-                # stream fresh scenarios: worlds pick them up at their next auto-reset (≙ test_case_fn per env.reset())
-                init, nag = self._new_scenarios()
-                self.rollout.env.set_reset_state(init, nag)
                 s = self.rollout.rec.pop_stats()
                 if self.dist:
                     t = self.torch.tensor([s["episodes"], s["score_sum"], s["frames"]], dtype=self.torch.float64, device="cuda")

@@ -231,6 +231,35 @@ class VecCollisionAvoidanceEnv(object):
             raise ValueError("out_obs must be a contiguous float32 CUDA tensor of shape (%d, %d, %d)" % (self.W, self.A, self.L))
         return out_obs
 
+    def scenario_config(self, test_case_args=None):
+        """ca_scenario_config from the reference's Config.TEST_CASE_ARGS dict (GCA/envs/config.py:50-62)."""
+        sc = _abi.CaScenarioConfig()
+        check(lib().ca_default_scenario_config(C.byref(sc), self.A), "ca_default_scenario_config")
+        a = test_case_args or {}
+        if 'speed_bnds' in a:
+            sc.speed_lo, sc.speed_hi = a['speed_bnds']
+        if 'radius_bnds' in a:
+            sc.radius_lo, sc.radius_hi = a['radius_bnds']
+        if a.get('num_agents'):
+            sc.min_agents = sc.max_agents = int(a['num_agents'])
+        pol = a.get('policies')
+        if pol is not None:
+            pol = [pol] if isinstance(pol, str) else list(pol)
+            distr = a.get('policy_distr') or [1.0 / len(pol)] * len(pol)
+            probs = {"noncoop": 0.0, "learning_ga3c": 0.0, "static": 0.0}
+            for name, pr in zip(pol, distr):
+                if name not in probs:
+                    raise NotImplementedError("policy %r is not available in the on-device generator" % name)
+                probs[name] += pr
+            sc.p_noncoop, sc.p_learning = probs["noncoop"], probs["learning_ga3c"]
+            sc.ensure_learner = 1 if a.get('policy_to_ensure') == 'learning_ga3c' else 0
+        return sc
+
+    def generate_scenarios(self, scenario_cfg, seed, only_consumed=False):
+        """On-device scenario generator (ca_generate_scenarios): refills the reset snapshot."""
+        check(lib().ca_generate_scenarios(self.handle._h, C.byref(scenario_cfg), int(seed) & (2 ** 64 - 1),
+                                          1 if only_consumed else 0, self._stream()), "ca_generate_scenarios")
+
     def reset(self, world_mask=None, out_obs=None):
         """out_obs: optional destination for the observation (e.g. a slot of a rollout's observation ring)."""
         obs = self._check_out_obs(out_obs)
