@@ -80,32 +80,37 @@ def test_generator_matches_reference_distribution(cls, A):
 
 
 def test_consumed_worlds_get_new_scenarios():
-    """Worlds that auto-reset take their snapshot; generate(only_consumed=True) refills exactly those."""
+    """ca_reset / auto-reset mark a world's snapshot as consumed; generate(only_consumed=True) refills exactly those,
+    so consecutive episodes of a world start from different scenarios, while without a refill they repeat."""
     import torch
     from rl_collision_avoidance_b200.vec_env import VecCollisionAvoidanceEnv
     W, A = 2048, 4
-    env = VecCollisionAvoidanceEnv(_abi.default_config(W, A, auto_reset=1))
-    sc = env.scenario_config({'policies': 'learning_ga3c'})
-    env.generate_scenarios(sc, seed=7)
-    env.reset()
-    first = env.get_state().copy()
-    gen = torch.Generator(device="cuda"); gen.manual_seed(1)
-    resets = np.zeros(W, dtype=int)
-    second_start = {}
-    for t in range(200):
-        a = torch.randint(0, 11, (W, A), dtype=torch.int32, device="cuda", generator=gen)
-        _, _, _, over = env.step(a)
-        o = over.cpu().numpy().astype(bool)
-        if o.any():
-            st = env.get_state()
-            for w in np.nonzero(o)[0]:
-                resets[w] += 1
-                if resets[w] == 1:      # first reset: the world restarts from the ORIGINAL snapshot
-                    np.testing.assert_array_equal(st[w, :, :_abi.S_TIME_REMAINING + 1], first[w, :, :_abi.S_TIME_REMAINING + 1])
-                elif resets[w] == 2:    # second reset: a new scenario generated after the first one was consumed
-                    second_start[w] = st[w].copy()
-        env.generate_scenarios(sc, seed=7, only_consumed=True)
-    assert len(second_start) > W // 4
-    differs = sum(1 for w, s in second_start.items() if not np.array_equal(s[:, :2], first[w, :, :2]))
-    assert differs == len(second_start)
-    env.close()
+    gen = torch.Generator(device="cuda")
+    for refill in (True, False):
+        env = VecCollisionAvoidanceEnv(_abi.default_config(W, A, auto_reset=1))
+        sc = env.scenario_config({'policies': 'learning_ga3c'})
+        env.generate_scenarios(sc, seed=7)
+        env.reset()
+        last_start = env.get_state()[:, :, :2].copy()
+        gen.manual_seed(1)
+        same = changed = 0
+        for t in range(150):
+            if refill:
+                env.generate_scenarios(sc, seed=7, only_consumed=True)
+            a = torch.randint(0, 11, (W, A), dtype=torch.int32, device="cuda", generator=gen)
+            _, _, _, over = env.step(a)
+            o = over.cpu().numpy().astype(bool)
+            if o.any():
+                st = env.get_state()[:, :, :2]
+                for w in np.nonzero(o)[0]:
+                    if np.array_equal(st[w], last_start[w]):
+                        same += 1
+                    else:
+                        changed += 1
+                    last_start[w] = st[w]
+        assert same + changed > W
+        if refill:
+            assert same == 0, "every new episode must start from a fresh scenario"
+        else:
+            assert changed == 0, "without a refill a world repeats its snapshot"
+        env.close()
