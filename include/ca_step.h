@@ -251,6 +251,14 @@ int ca_ga3c_episode_stats(const float* obs_now, const float* reward, const uint8
                           int32_t* ep_steps, double* stats, int32_t num_worlds, int32_t agents_per_world,
                           int32_t obs_len, int device, void* stream);
 
+/* One fused LSTM time step of the predictor (ThreadPredictor / NetworkVP_rnn forward, GA3C/NetworkVP_rnn.py:58-66), device
+ * pointers, float32: obs rows [B][obs_stride] (raw observation: column 1 = num_other_agents, other agent t at columns
+ * 6+7t..6+7t+6), zh = h @ kernel[7:71] of the previous state ([B][256], NULL when h = 0), Kx = kernel[0:7] ([7][256]),
+ * bias [256], avg7/std7 = normalisation of the 7 other-agent columns, c/h [B][64] updated in place. */
+int ca_lstm_step(const float* obs, int32_t obs_stride, const float* zh, const float* Kx, const float* bias,
+                 const float* avg7, const float* std7, float* c, float* h, int32_t batch, int32_t t, int device,
+                 void* stream);
+
 const char* ca_strerror(int code);
 const char* ca_last_error(void);
 int ca_abi_version(void);

@@ -26,7 +26,7 @@ NVCC_FLAGS = [
 EXPORTS = [
     "ca_default_config", "ca_create", "ca_destroy", "ca_set_world_state", "ca_set_reset_state", "ca_reset", "ca_step", "ca_step_host",
     "ca_reset_host", "ca_get_state", "ca_launch_count", "ca_host_alloc", "ca_host_free", "ca_nstep_returns",
-    "ca_ga3c_record", "ca_ga3c_episode_stats", "ca_default_scenario_config", "ca_generate_scenarios",
+    "ca_ga3c_record", "ca_ga3c_episode_stats", "ca_default_scenario_config", "ca_generate_scenarios", "ca_lstm_step",
     "ca_strerror", "ca_last_error", "ca_abi_version",
 ]
 
@@ -94,6 +94,7 @@ def lib():
     L.ca_ga3c_episode_stats.argtypes = [vp, vp, vp, vp, vp, vp, i32, i32, i32, C.c_int, vp]
     L.ca_default_scenario_config.argtypes = [C.POINTER(_abi.CaScenarioConfig), i32]
     L.ca_generate_scenarios.argtypes = [vp, C.POINTER(_abi.CaScenarioConfig), C.c_uint64, C.c_int, vp]
+    L.ca_lstm_step.argtypes = [vp, i32, vp, vp, vp, vp, vp, vp, vp, i32, i32, C.c_int, vp]
     L.ca_strerror.argtypes = [C.c_int]
     L.ca_strerror.restype = C.c_char_p
     L.ca_last_error.restype = C.c_char_p

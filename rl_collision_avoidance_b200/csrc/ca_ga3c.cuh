@@ -146,3 +146,49 @@ __global__ void ga3c_episode_stats_kernel(const float* __restrict__ obs_now, con
 }
 
 }  // namespace ca
+
+namespace ca {
+
+// One LSTM time step of the predictor, fused: input projection (7 -> 256, weights in shared memory), recurrent
+// pre-activation add, gates, state update and the dynamic_rnn sequence-length mask in a single pass.
+// TF-1.15 LSTMCell semantics (GA3C/NetworkVP_rnn.py:63-66): gate order i, j, f, o; c' = sigmoid(f + 1) c + sigmoid(i) tanh(j);
+// h' = sigmoid(o) tanh(c'); rows with t >= num_other_agents keep their state.  Reads the raw observation rows
+// (stride obs_stride floats; num_other_agents at column 1, the t-th other agent at columns 6 + 7t .. 6 + 7t + 6) and
+// normalises on the fly with (x - avg) / std, so no normalised copy of the observations is ever materialised.
+__global__ void __launch_bounds__(256) lstm_step_kernel(const float* __restrict__ obs, int obs_stride,
+                                                        const float* __restrict__ zh, const float* __restrict__ Kx,
+                                                        const float* __restrict__ bias, const float* __restrict__ avg7,
+                                                        const float* __restrict__ std7, float* __restrict__ c,
+                                                        float* __restrict__ h, int B, int t) {
+  __shared__ float sK[7 * 256];
+  __shared__ float sb[256];
+  __shared__ float sa[7], ss[7];
+  for (int q = threadIdx.x; q < 7 * 256; q += 256) sK[q] = Kx[q];
+  sb[threadIdx.x] = bias[threadIdx.x];
+  if (threadIdx.x < 7) { sa[threadIdx.x] = avg7[threadIdx.x]; ss[threadIdx.x] = std7[threadIdx.x]; }
+  __syncthreads();
+  const int u = threadIdx.x & 63;
+  const long row = (long)blockIdx.x * 4 + (threadIdx.x >> 6);
+  if (row >= B) return;
+  const float* o = obs + row * obs_stride;
+  if (!(o[1] > (float)t)) return;  // sequence_length = raw num_other_agents
+  float x[7];
+#pragma unroll
+  for (int k = 0; k < 7; ++k) x[k] = (o[6 + 7 * t + k] - sa[k]) / ss[k];
+  float g[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int col = q * 64 + u;
+    float z = sb[col] + (zh ? zh[row * 256 + col] : 0.f);
+#pragma unroll
+    for (int k = 0; k < 7; ++k) z += x[k] * sK[k * 256 + col];
+    g[q] = z;
+  }
+  const float cp = c[row * 64 + u];
+  const float sig_i = 1.f / (1.f + expf(-g[0])), sig_f = 1.f / (1.f + expf(-(g[2] + 1.f))), sig_o = 1.f / (1.f + expf(-g[3]));
+  const float cn = sig_f * cp + sig_i * tanhf(g[1]);
+  c[row * 64 + u] = cn;
+  h[row * 64 + u] = sig_o * tanhf(cn);
+}
+
+}  // namespace ca

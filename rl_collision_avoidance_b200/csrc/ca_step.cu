@@ -688,4 +688,17 @@ int ca_ga3c_episode_stats(const float* obs_now, const float* reward, const uint8
   return CA_OK;
 }
 
+int ca_lstm_step(const float* obs, int32_t obs_stride, const float* zh, const float* Kx, const float* bias,
+                 const float* avg7, const float* std7, float* c, float* h, int32_t batch, int32_t t, int device,
+                 void* stream) {
+  if (!obs || !Kx || !bias || !avg7 || !std7 || !c || !h || batch < 1 || t < 0 || obs_stride < 6 + 7 * (t + 1))
+    return fail(CA_ERR_INVALID_ARG, "bad argument");
+  DeviceGuard guard(device);
+  if (!guard.ok) return fail(CA_ERR_CUDA, "cudaSetDevice(%d) failed", device);
+  ca::lstm_step_kernel<<<(batch + 3) / 4, 256, 0, (cudaStream_t)stream>>>(obs, obs_stride, zh, Kx, bias, avg7, std7, c, h,
+                                                                          batch, t);
+  CA_CUDA(cudaPeekAtLastError());
+  return CA_OK;
+}
+
 }  // extern "C"

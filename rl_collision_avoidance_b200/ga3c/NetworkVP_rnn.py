@@ -167,6 +167,45 @@ class NetworkVP_rnn(object):
         p, v, _ = self.net(x)
         return p, v
 
+    @torch.no_grad()
+    def predict_from_obs(self, obs):
+        """Predictor on raw observation rows obs [B, L] (column 0 = is_learning), CUDA only: the LSTM runs through the
+        fused ca_lstm_step kernel (input projection + gates + state update + sequence mask in one pass per step, no
+        normalised or per-gate intermediates in HBM); the dense layers are cuBLAS GEMMs.  Same function as
+        `predict_p_and_v_device(obs[:, 1:])` (tests/test_gpu_ga3c.py checks them against each other)."""
+        import ctypes as C
+        from .._lib import check, lib
+        net = self.net
+        B, L = obs.shape
+        if not obs.is_cuda or obs.dtype != torch.float32 or obs.stride(1) != 1:
+            raise ValueError("obs must be a float32 CUDA tensor with contiguous rows")
+        H, M = net.HIDDEN, net.M
+        K = net.w("rnn/lstm_cell/kernel")
+        Kx, Kh = K[:net.other_len].contiguous(), K[net.other_len:].contiguous()
+        bias = net.w("rnn/lstm_cell/bias")
+        off = net.first + net.host_len                      # first other-agent column of the NN input
+        avg7, std7 = net.avg[off:off + 7].contiguous(), net.std[off:off + 7].contiguous()
+        c = torch.zeros((B, H), dtype=torch.float32, device=obs.device)
+        h = torch.zeros((B, H), dtype=torch.float32, device=obs.device)
+        p_ = lambda t: C.c_void_p(t.data_ptr())
+        stream = C.c_void_p(torch.cuda.current_stream(obs.device).cuda_stream)
+        dev = obs.device.index or 0
+        zh = None
+        for t in range(M):
+            if t > 0:
+                zh = h @ Kh
+            check(lib().ca_lstm_step(p_(obs), int(obs.stride(0)), p_(zh) if zh is not None else None, p_(Kx), p_(bias),
+                                     p_(avg7), p_(std7), p_(c), p_(h), B, t, dev, stream), "ca_lstm_step")
+        host = (obs[:, 1 + net.first:1 + net.first + net.host_len] - net.avg[net.first:net.first + net.host_len]) \
+            / net.std[net.first:net.first + net.host_len]
+        a = torch.relu(torch.addmm(net.w("layer1/bias"), torch.cat([host, h], dim=1), net.w("layer1/kernel")))
+        a = torch.relu(torch.addmm(net.w("layer2/bias"), a, net.w("layer2/kernel")))
+        a = torch.relu(torch.addmm(net.w("fullyconnected1/bias"), a, net.w("fullyconnected1/kernel")))
+        logits = torch.addmm(net.w("logits_p/bias"), a, net.w("logits_p/kernel"))
+        v = torch.addmv(net.w("logits_v/bias"), a, net.w("logits_v/kernel").squeeze(1))
+        p = (torch.softmax(logits, dim=1) + net.min_policy) / (1.0 + net.min_policy * net.num_actions)
+        return p, v
+
     def predict_p_and_v(self, x):
         p, v = self.predict_p_and_v_device(self._as_input(x))
         return p.cpu().numpy(), v.cpu().numpy()

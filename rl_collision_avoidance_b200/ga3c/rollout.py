@@ -110,8 +110,7 @@ class GpuRollout(object):
         """One env step for every world; returns (reward, done, game_over) device tensors of this step."""
         torch = self.torch
         obs = self.rec.obs_slot(self.t)                           # [W, A, L]; column 0 = is_learning
-        x = obs.reshape(self.N, self.L)[:, 1:]
-        p, v = self.model.predict_p_and_v_device(x)               # ThreadPredictor: one batch over all slots
+        p, v = self.model.predict_from_obs(obs.reshape(self.N, self.L))   # ThreadPredictor: one batch over all slots
         if self.greedy:
             actions = torch.argmax(p, dim=1).to(torch.int32)      # ProcessAgent.select_action (:98-103)
         else:

@@ -221,6 +221,33 @@ def test_rollout_rows_rederived_on_cpu(phase1_cfg):
     ro.close()
 
 
+def test_fused_lstm_predictor_matches_torch_and_numpy(phase1_cfg):
+    """predict_from_obs (ca_lstm_step kernel + cuBLAS dense layers) == the plain PyTorch forward == the NumPy oracle."""
+    import torch
+    from oracle import network_oracle
+    from rl_collision_avoidance_b200.ga3c.NetworkVP_rnn import NetworkVP_rnn
+    from tests.test_pretrained_policy import load_iros18
+    cfg = phase1_cfg
+    rng = np.random.default_rng(0)
+    net = NetworkVP_rnn("cuda:0", "network", 11, seed=2)
+    net.net.load_tf_variables(load_iros18())
+    B, L = 5003, 27
+    obs = rng.normal(size=(B, L)).astype(np.float32) * 2
+    obs[:, 0] = 1
+    obs[:, 1] = rng.integers(0, 4, B)
+    t_obs = torch.from_numpy(obs).cuda()
+    p1, v1 = net.predict_from_obs(t_obs)
+    p2, v2 = net.predict_p_and_v_device(t_obs[:, 1:])
+    assert torch.allclose(p1, p2, atol=2e-6) and torch.allclose(v1, v2, atol=2e-5)
+    p3, v3 = network_oracle.forward(net.net.tf_variables(), obs[:, 1:], cfg.NN_INPUT_AVG_VECTOR, cfg.NN_INPUT_STD_VECTOR, 3)
+    np.testing.assert_allclose(p1.cpu().numpy(), p3, atol=5e-6)
+    np.testing.assert_allclose(v1.cpu().numpy(), v3, atol=5e-5)
+    # a strided view of a wider buffer (the rollout's observation ring) works too
+    wide = torch.zeros((B, L + 5), device="cuda"); wide[:, :L] = t_obs
+    p4, _ = net.predict_from_obs(wide[:, :L])
+    assert torch.equal(p4, p1)
+
+
 def test_server_main_trains(phase1_cfg, tmp_path, monkeypatch):
     monkeypatch.setenv("GA3C_CHECKPOINT_DIR", str(tmp_path))
     from rl_collision_avoidance_b200.ga3c.Server import Server
