@@ -240,8 +240,9 @@ def test_fused_lstm_predictor_matches_torch_and_numpy(phase1_cfg):
     p2, v2 = net.predict_p_and_v_device(t_obs[:, 1:])
     assert torch.allclose(p1, p2, atol=2e-6) and torch.allclose(v1, v2, atol=2e-5)
     p3, v3 = network_oracle.forward(net.net.tf_variables(), obs[:, 1:], cfg.NN_INPUT_AVG_VECTOR, cfg.NN_INPUT_STD_VECTOR, 3)
-    np.testing.assert_allclose(p1.cpu().numpy(), p3, atol=5e-6)
-    np.testing.assert_allclose(v1.cpu().numpy(), v3, atol=5e-5)
+    # float32 network with the trained (large) weights vs the float64 oracle: a few 1e-6 of accumulated rounding
+    np.testing.assert_allclose(p1.cpu().numpy(), p3, rtol=0, atol=3e-5)
+    np.testing.assert_allclose(v1.cpu().numpy(), v3, rtol=0, atol=3e-4)
     # a strided view of a wider buffer (the rollout's observation ring) works too
     wide = torch.zeros((B, L + 5), device="cuda"); wide[:, :L] = t_obs
     p4, _ = net.predict_from_obs(wide[:, :L])
