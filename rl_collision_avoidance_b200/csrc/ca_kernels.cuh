@@ -76,12 +76,12 @@ __device__ __forceinline__ double dot2(double a0, double a1, double b0, double b
 }
 
 struct Ego {
-  double dist, hego, prx, pry;  // orth = (-pry, prx)
+  double dist, prx, pry;  // orth = (-pry, prx)
+  float hego;             // heading_ego_frame as it goes into the float32 observation
 };
 
-// Agent.get_ref (GCA/envs/agent.py:326-346) + Dynamics.update_ego_frame (GCA/envs/dynamics/Dynamics.py:24-41)
-__device__ __forceinline__ Ego ego_frame(double px, double py, double gx, double gy, double hd) {
-  Ego e;
+// Agent.get_ref (GCA/envs/agent.py:326-346): distance to goal and the ego-frame axes, float64.
+__device__ __forceinline__ void ego_axes(double px, double py, double gx, double gy, Ego& e) {
   const double dx = gx - px, dy = gy - py;
   e.dist = sqrt(dx * dx + dy * dy);
   if (e.dist > 1e-8) {
@@ -91,7 +91,29 @@ __device__ __forceinline__ Ego ego_frame(double px, double py, double gx, double
     e.prx = dx;
     e.pry = dy;
   }
-  e.hego = wrap_angle(hd - atan2(e.pry, e.prx));
+}
+
+// heading_ego_frame = wrap(heading - atan2(ref_prll)) (GCA/envs/dynamics/Dynamics.py:31-35) in float64: this is the
+// value the non-cooperative policy turns into its command, i.e. it feeds the dynamics and must be exact.
+__device__ __forceinline__ double heading_ego_exact(const Ego& e, double hd) {
+  return wrap_angle(hd - atan2(e.pry, e.prx));
+}
+
+// The same quantity for the observation vector.  Observations are float32 (tolerance 1e-5); nothing downstream of
+// the env reads it back, so it is evaluated with the float32 atan2 (|error| < 1e-6 rad) which is ~4x cheaper than the
+// float64 one and sits at the end of the kernel's longest dependency chain.
+__device__ __forceinline__ float heading_ego_obs(const Ego& e, double hd) {
+  const float pi = 3.14159265358979323846f;
+  float a = (float)hd - atan2f((float)e.pry, (float)e.prx);
+  if (a >= pi) a -= 2.f * pi;
+  if (a < -pi) a += 2.f * pi;
+  return a;
+}
+
+__device__ __forceinline__ Ego ego_frame(double px, double py, double gx, double gy, double hd) {
+  Ego e;
+  ego_axes(px, py, gx, gy, e);
+  e.hego = heading_ego_obs(e, hd);
   return e;
 }
 
@@ -258,7 +280,7 @@ __device__ __forceinline__ void write_obs_row(const Params& p, const Smem& sm, c
       row[0] = (a.policy == CA_POLICY_LEARNING_GA3C || a.policy == CA_POLICY_LEARNING) ? 1.f : 0.f;
       row[1] = (float)count;
       row[2] = (float)e.dist;
-      row[3] = (float)e.hego;
+      row[3] = e.hego;
       row[4] = (float)a.ps;
       row[5] = (float)a.rad;
       for (int q = CA_OBS_HOST_LEN + CA_OBS_OTHER_LEN * count; q < p.L; ++q) row[q] = 0.f;
@@ -365,9 +387,10 @@ __global__ void __launch_bounds__(kBlock) ca_world_kernel(const __grid_constant_
       if (a.policy == CA_POLICY_NONCOOP) {
         // NonCooperativePolicy.find_next_action (policies/NonCooperativePolicy.py:9-22) reads the ego
         // heading of the pre-step state
-        const Ego e0 = ego_frame(a.px, a.py, a.gx, a.gy, a.hd);
+        Ego e0;
+        ego_axes(a.px, a.py, a.gx, a.gy, e0);
         cmd_speed = (float)a.ps;
-        cmd_dh = (float)(-e0.hego);
+        cmd_dh = (float)(-heading_ego_exact(e0, a.hd));
       } else if (a.policy == CA_POLICY_LEARNING_GA3C) {  // LearningPolicyGA3C.external_action_to_action
         int k = p.actions[g];
         k = k < 0 ? 0 : (k > 10 ? 10 : k);

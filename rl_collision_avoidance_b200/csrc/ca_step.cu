@@ -200,8 +200,10 @@ int default_pipe_min_blocks(int A) {
   }
 }
 
-const void* pipe_kernel_ptr(int A, int mb) {
-#define X(a, b) if (A == a && mb == b) return (const void*)ca::ca_step_pipe_kernel<a, b>;
+const void* pipe_kernel_ptr(int A, int mb, bool dbg = false) {
+#define X(a, b)          \
+  if (A == a && mb == b) \
+    return dbg ? (const void*)ca::ca_step_pipe_kernel<a, b, true> : (const void*)ca::ca_step_pipe_kernel<a, b, false>;
   CA_PIPE_VARIANTS(X)
 #undef X
   return nullptr;
@@ -222,14 +224,15 @@ int default_oneshot_min_blocks(int A) {
   }
 }
 
-const void* fast_kernel_ptr(int A) {
+const void* fast_kernel_ptr(int A, bool dbg) {
   int mb = default_oneshot_min_blocks(A);
   const char* env = getenv("CA_ONESHOT_MINBLOCKS");
   const int v = env ? atoi(env) : 0;
 #define X(a, b) if (A == a && v == b) mb = v;
   CA_ONESHOT_VARIANTS(X)
 #undef X
-#define X(a, b) if (A == a && mb == b) return (const void*)ca::ca_step_kernel<a, b>;
+#define X(a, b) \
+  if (A == a && mb == b) return dbg ? (const void*)ca::ca_step_kernel<a, b, true> : (const void*)ca::ca_step_kernel<a, b, false>;
   CA_ONESHOT_VARIANTS(X)
 #undef X
   return nullptr;
@@ -238,8 +241,13 @@ const void* fast_kernel_ptr(int A) {
 // Launch with the programmatic-stream-serialization attribute (PDL): back-to-back steps overlap the launch latency
 // and ramp-up of step t+1 with the tail of step t; the kernels call griddepcontrol.wait before touching global data.
 cudaError_t set_fast_smem_attr(int A, int bytes) {
-  const void* fn = fast_kernel_ptr(A);
-  return fn ? cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes) : cudaSuccess;
+  for (int dbg = 0; dbg < 2; ++dbg) {
+    const void* fn = fast_kernel_ptr(A, dbg != 0);
+    if (!fn) continue;
+    cudaError_t ce = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (ce != cudaSuccess) return ce;
+  }
+  return cudaSuccess;
 }
 
 int launch_pdl(const void* fn, int grid, size_t smem, cudaStream_t st, ca::Params& p, bool pdl) {
@@ -263,12 +271,14 @@ int launch_world_kernel(ca_env* e, bool step, ca::Params& p, cudaStream_t st) {
   p.use_bulk_store = (e->bulk_ok && aligned16(p.obs) && (e->tile_floats % 4) == 0) ? 1 : 0;
   p.warp_store = ((e->tile_floats / kWarps) % 4) == 0 ? 1 : 0;
   int rc;
+  // the instantiations with neighbour-index output / finite sensing horizon are only used when asked for
+  const bool dbg = p.sidx != nullptr || std::isfinite(e->cfg.sensing_horizon);
   if (step && has_fast_kernel(e) && e->kernel_choice == 0) {
     p.use_bulk_store = (e->bulk_ok && aligned16(p.obs)) ? 1 : 0;  // per-warp tile; its own size check is in-kernel
-    rc = launch_pdl(pipe_kernel_ptr(e->A, e->pipe_min_blocks), e->pipe_grid, e->smem_pipe, st, p, e->use_pdl);
+    rc = launch_pdl(pipe_kernel_ptr(e->A, e->pipe_min_blocks, dbg), e->pipe_grid, e->smem_pipe, st, p, e->use_pdl);
   } else if (step && has_fast_kernel(e)) {
     if (e->store_vec4 && aligned16(p.obs) && p.warp_store) p.use_bulk_store = 2;
-    rc = launch_pdl(fast_kernel_ptr(e->A), e->grid, e->smem_fast, st, p, e->use_pdl);
+    rc = launch_pdl(fast_kernel_ptr(e->A, dbg), e->grid, e->smem_fast, st, p, e->use_pdl);
   } else if (step) {
     rc = launch_pdl((const void*)ca::ca_world_kernel<true>, e->grid, e->smem_bytes, st, p, e->use_pdl);
   } else {
@@ -409,6 +419,9 @@ int ca_create(const ca_config* cfg, ca_env** out) {
     const int warp_tile_bytes = ((e->tile_floats / kWarps) * 4 + 15) / 16 * 16;
     e->smem_pipe = (size_t)kWarps * (ca::kStageBytes + warp_tile_bytes + 16);
     ce = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem_pipe);
+    if (ce == cudaSuccess)
+      ce = cudaFuncSetAttribute(pipe_kernel_ptr(e->A, e->pipe_min_blocks, true), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)e->smem_pipe);
     int per_sm = 0, sms = 0;
     if (ce == cudaSuccess) ce = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, kBlock, e->smem_pipe);
     if (ce == cudaSuccess) ce = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, cfg->device);

@@ -107,7 +107,7 @@ __device__ __forceinline__ void fast_write_obs_row(const Params& p, const Agent&
       row[0] = (a.policy == CA_POLICY_LEARNING_GA3C || a.policy == CA_POLICY_LEARNING) ? 1.f : 0.f;
       row[1] = (float)count;
       row[2] = (float)e.dist;
-      row[3] = (float)e.hego;
+      row[3] = e.hego;
       row[4] = (float)a.ps;
       row[5] = (float)a.rad;
       for (int q = CA_OBS_HOST_LEN + CA_OBS_OTHER_LEN * count; q < p.L; ++q) row[q] = 0.f;
@@ -169,7 +169,7 @@ __device__ __forceinline__ void fast_store_warp_tile(const Params& p, const floa
   for (int q = lane; q < nfloats; q += 32) dst[q] = wtile[q];
 }
 
-template <int kA, int kMinBlocks = 1>
+template <int kA, int kMinBlocks, bool kDbg>
 __global__ void __launch_bounds__(kBlock, kMinBlocks) ca_step_kernel(const __grid_constant__ Params p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   constexpr int wpw = 32 / kA;
@@ -208,9 +208,10 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks) ca_step_kernel(const __gri
   float cmd_speed = 0.f, cmd_dh = 0.f;
   if (valid && !was_done) {
     if (a.policy == CA_POLICY_NONCOOP) {
-      const Ego e0 = ego_frame(a.px, a.py, a.gx, a.gy, a.hd);
+      Ego e0;
+      ego_axes(a.px, a.py, a.gx, a.gy, e0);
       cmd_speed = (float)a.ps;
-      cmd_dh = (float)(-e0.hego);
+      cmd_dh = (float)(-heading_ego_exact(e0, a.hd));
     } else if (a.policy == CA_POLICY_LEARNING_GA3C) {
       const int k = act < 0 ? 0 : (act > 10 ? 10 : act);
       cmd_speed = (float)(a.ps * kActSpeed[k]);
@@ -253,7 +254,7 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks) ca_step_kernel(const __gri
   OthersLite<kA> o;
   bool coll;
   double nearest;
-  pipe_pair_pass<kA, true>(p, a, e, valid, n, i, base, o, coll, nearest);
+  pipe_pair_pass<kA, true, kDbg>(p, a, e, valid, n, i, base, o, coll, nearest);
 
   // ---- _compute_rewards (:319-368)
   double r = p.r_step;
@@ -290,7 +291,7 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks) ca_step_kernel(const __gri
   const bool do_reset = world_ok && over && p.auto_reset;
 
   if (!__any_sync(kFull, do_reset)) {
-    pipe_write_obs_row<kA>(p, a, e, world_ok, valid, i, base, o, row, sidx_row);
+    pipe_write_obs_row<kA, kDbg>(p, a, e, world_ok, valid, i, base, o, row, sidx_row);
   } else {
     // DummyVecEnv semantics: worlds that finished reload their injected initial state and observe again;
     // the other worlds of the warp observe their post-step state.
@@ -303,8 +304,8 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks) ca_step_kernel(const __gri
     }
     bool c_unused;
     double n_unused;
-    pipe_pair_pass<kA, false>(p, a, e, valid, n, i, base, o, c_unused, n_unused);
-    pipe_write_obs_row<kA>(p, a, e, world_ok, valid, i, base, o, row, sidx_row);
+    pipe_pair_pass<kA, false, kDbg>(p, a, e, valid, n, i, base, o, c_unused, n_unused);
+    pipe_write_obs_row<kA, kDbg>(p, a, e, world_ok, valid, i, base, o, row, sidx_row);
   }
 
   // ---- state write-back

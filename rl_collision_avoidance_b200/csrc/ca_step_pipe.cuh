@@ -56,12 +56,14 @@ struct OthersLite {
   double d[kN];     // centre distance
 };
 
-template <int kA, bool kCollide>
+// kDbg selects the rarely used features (finite SENSING_HORIZON, neighbour-index output for parity tests); the
+// production instantiation (kDbg = false) carries neither their instructions nor their registers.
+template <int kA, bool kCollide, bool kDbg>
 __device__ __forceinline__ void pipe_pair_pass(const Params& p, const Agent& a, const Ego& e, bool valid, int n, int i,
                                                int base, OthersLite<kA>& o, bool& coll, double& nearest) {
   coll = false;
   nearest = INFINITY;
-  const bool horizon = isfinite(p.sensing_horizon);
+  const bool horizon = kDbg && isfinite(p.sensing_horizon);
 #pragma unroll
   for (int k = 0; k < kA - 1; ++k) {
     const int j = k + (k >= i ? 1 : 0);
@@ -86,10 +88,11 @@ __device__ __forceinline__ bool key_first(int q1, double p1, int q2, double p2) 
   return (q1 < q2) || (q1 == q2 && p1 <= p2);
 }
 
-template <int kA>
+template <int kA, bool kDbg>
 __device__ __forceinline__ void pipe_write_obs_row(const Params& p, const Agent& a, const Ego& e, bool world_ok,
                                                    bool valid, int i, int base, const OthersLite<kA>& o, float* row,
-                                                   int32_t* sidx_row) {
+                                                   int32_t* sidx_row_in) {
+  int32_t* const sidx_row = kDbg ? sidx_row_in : nullptr;
   constexpr int kN = kA - 1;
   constexpr int kNN = kN > 0 ? kN : 1;
   const int M = p.M;
@@ -138,7 +141,7 @@ __device__ __forceinline__ void pipe_write_obs_row(const Params& p, const Agent&
       row[0] = (a.policy == CA_POLICY_LEARNING_GA3C || a.policy == CA_POLICY_LEARNING) ? 1.f : 0.f;
       row[1] = (float)count;
       row[2] = (float)e.dist;
-      row[3] = (float)e.hego;
+      row[3] = e.hego;
       row[4] = (float)a.ps;
       row[5] = (float)a.rad;
       for (int q = CA_OBS_HOST_LEN + CA_OBS_OTHER_LEN * count; q < p.L; ++q) row[q] = 0.f;
@@ -169,7 +172,7 @@ __device__ __forceinline__ void pipe_write_obs_row(const Params& p, const Agent&
   }
 }
 
-template <int kA, int kMinBlocks>
+template <int kA, int kMinBlocks, bool kDbg>
 __global__ void __launch_bounds__(kBlock, kMinBlocks) ca_step_pipe_kernel(const __grid_constant__ Params p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   constexpr int wpw = 32 / kA;
@@ -266,9 +269,10 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks) ca_step_pipe_kernel(const 
     float cmd_speed = 0.f, cmd_dh = 0.f;
     if (valid && !was_done) {
       if (a.policy == CA_POLICY_NONCOOP) {
-        const Ego e0 = ego_frame(a.px, a.py, a.gx, a.gy, a.hd);
+        Ego e0;
+        ego_axes(a.px, a.py, a.gx, a.gy, e0);
         cmd_speed = (float)a.ps;
-        cmd_dh = (float)(-e0.hego);
+        cmd_dh = (float)(-heading_ego_exact(e0, a.hd));
       } else if (a.policy == CA_POLICY_LEARNING_GA3C) {
         const int k = act < 0 ? 0 : (act > 10 ? 10 : act);
         cmd_speed = (float)(a.ps * kActSpeed[k]);
@@ -311,7 +315,7 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks) ca_step_pipe_kernel(const 
     OthersLite<kA> o;
     bool coll;
     double nearest;
-    pipe_pair_pass<kA, true>(p, a, e, valid, n, i, base, o, coll, nearest);
+    pipe_pair_pass<kA, true, kDbg>(p, a, e, valid, n, i, base, o, coll, nearest);
 
     // ---- _compute_rewards (:319-368)
     double r = p.r_step;
@@ -357,7 +361,7 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks) ca_step_pipe_kernel(const 
       }
       bool c_unused;
       double n_unused;
-      pipe_pair_pass<kA, false>(p, a, e, valid, n, i, base, o, c_unused, n_unused);
+      pipe_pair_pass<kA, false, kDbg>(p, a, e, valid, n, i, base, o, c_unused, n_unused);
     }
 
     // the tile still feeds the previous chunk's bulk store until that store has read it
@@ -366,7 +370,7 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks) ca_step_pipe_kernel(const 
       __syncwarp();
       store_pending = false;
     }
-    pipe_write_obs_row<kA>(p, a, e, world_ok, valid, i, base, o, row, sidx_row);
+    pipe_write_obs_row<kA, kDbg>(p, a, e, world_ok, valid, i, base, o, row, sidx_row);
 
     // ---- state write-back (coalesced)
     if (valid || do_reset) {
