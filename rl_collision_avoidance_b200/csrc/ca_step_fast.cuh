@@ -1,141 +1,19 @@
-// ca_step_fast.cuh — the step kernel specialised on the number of agent slots per world (kA).
+// ca_step_fast.cuh — the one-shot step kernel specialised on the number of agent slots per world (kA): the default.
 //
 // Same algorithm, data layout and numerics as ca_world_kernel<true> (ca_kernels.cuh), but with kA a
-// compile-time constant every per-other loop is fully unrolled: the lane's sort keys, relative positions
-// and centre distances of its (kA-1) potential neighbours live in registers, the neighbour order is a
-// pairwise rank (each unordered pair of keys is compared once) and nothing but the finished observation
-// rows goes through shared memory.  Used for closest_first / closest_last sorting; time_to_impact sorting,
-// reset, and agent counts without an instantiation run on the generic kernel.
+// compile-time constant every per-other loop is fully unrolled: the lane's int32 sort keys, p_orth and centre
+// distances of its (kA-1) potential neighbours live in registers (shared with ca_step_pipe.cuh: pipe_pair_pass /
+// pipe_write_obs_row), the neighbour order is a pairwise rank (each unordered pair of keys is compared once) and
+// nothing but the finished observation rows goes through shared memory; each warp hands its rows to one TMA bulk
+// store.  One CTA = 4 warps = 4 chunks of floor(32/kA) worlds; the launch-bounds occupancy target (kMinBlocks) is
+// tuned per kA so that the grid finishes in as few rounds of resident warps as possible.  Used for closest_first /
+// closest_last sorting; time_to_impact sorting, reset, and agent counts without an instantiation run on the
+// generic kernel.
 #pragma once
 #include "ca_kernels.cuh"
 #include "ca_step_pipe.cuh"
 
 namespace ca {
-
-template <int kA>
-struct Others {
-  static constexpr int kN = kA > 1 ? kA - 1 : 1;
-  double key[kN];   // signed rint(100 * dist_2_other); +inf for an absent / unobserved other
-  double po[kN];    // p_orth
-  double d[kN];     // centre distance
-  double rx[kN], ry[kN], rr[kN];  // relative position and radius of the other
-};
-
-// Sensor first loop (OtherAgentsStatesSensor.sense :72-103) + _check_for_collisions (:370-409) for the lane's
-// agent against its k-th other, j = k + (k >= i).  All lanes of the warp execute the shuffles.
-template <int kA, bool kCollide>
-__device__ __forceinline__ void fast_pair_pass(const Params& p, const Agent& a, const Ego& e, bool valid, int n, int i,
-                                               int base, Others<kA>& o, bool& coll, double& nearest) {
-  coll = false;
-  nearest = INFINITY;
-  const bool horizon = isfinite(p.sensing_horizon);
-#pragma unroll
-  for (int k = 0; k < kA - 1; ++k) {
-    const int j = k + (k >= i ? 1 : 0);
-    const int src = (base + j) & 31;
-    const double xj = shfl_d(a.px, src), yj = shfl_d(a.py, src), rj = shfl_d(a.rad, src);
-    const bool live = valid && j < n;
-    const double rx = xj - a.px, ry = yj - a.py;
-    const double d = sqrt(rx * rx + ry * ry);  // l2norm / vec2_l2_norm (util.py:8-12,106-112)
-    if (kCollide && live) {
-      const double R = a.rad + rj;
-      if (d <= R) coll = true;
-      if (j > i) nearest = fmin(nearest, d - R);  // only the lower index is updated (:393)
-    }
-    const bool seen = live && !(horizon && d > p.sensing_horizon);
-    o.key[k] = seen ? rint((d - a.rad - rj) * 100.0) : INFINITY;
-    o.po[k] = dot2(rx, ry, -e.pry, e.prx);
-    o.d[k] = d;
-    o.rx[k] = rx; o.ry[k] = ry; o.rr[k] = rj;
-  }
-}
-
-// (key, p_orth, list position) strict order; k1 < k2 so a full tie keeps k1 first (stable sort).
-__device__ __forceinline__ bool first_before_second(double q1, double p1, double q2, double p2) {
-  return (q1 < q2) || (q1 == q2 && p1 <= p2);
-}
-
-template <int kA>
-__device__ __forceinline__ void fast_write_obs_row(const Params& p, const Agent& a, const Ego& e, bool world_ok,
-                                                   bool valid, int i, int base, const Others<kA>& o, float* row,
-                                                   int32_t* sidx_row) {
-  constexpr int kN = kA - 1;
-  const int M = p.M;
-  int count = 0;
-#pragma unroll
-  for (int k = 0; k < kN; ++k) count += (o.key[k] < INFINITY) ? 1 : 0;
-  double key[kN > 0 ? kN : 1];
-#pragma unroll
-  for (int k = 0; k < kN; ++k) key[k] = o.key[k];
-  if (count > M) {
-    // first sort by (round(dist), p_orth) and keep the M closest (get_clipped_sorted_inds :31-38)
-    int rank1[kN > 0 ? kN : 1];
-#pragma unroll
-    for (int k = 0; k < kN; ++k) rank1[k] = 0;
-#pragma unroll
-    for (int k1 = 0; k1 < kN; ++k1)
-#pragma unroll
-      for (int k2 = k1 + 1; k2 < kN; ++k2) {
-        const bool b = first_before_second(o.key[k1], o.po[k1], o.key[k2], o.po[k2]);
-        rank1[k1] += b ? 0 : 1;
-        rank1[k2] += b ? 1 : 0;
-      }
-#pragma unroll
-    for (int k = 0; k < kN; ++k)
-      if (rank1[k] >= M) key[k] = INFINITY;
-    count = M;
-  }
-  if (p.sort_method == CA_SORT_CLOSEST_LAST) {  // final order by (-round(dist), p_orth) (:41-43)
-#pragma unroll
-    for (int k = 0; k < kN; ++k)
-      if (key[k] < INFINITY) key[k] = -key[k];
-  }
-  int slot[kN > 0 ? kN : 1];
-#pragma unroll
-  for (int k = 0; k < kN; ++k) slot[k] = 0;
-#pragma unroll
-  for (int k1 = 0; k1 < kN; ++k1)
-#pragma unroll
-    for (int k2 = k1 + 1; k2 < kN; ++k2) {
-      const bool b = first_before_second(key[k1], o.po[k1], key[k2], o.po[k2]);
-      slot[k1] += b ? 0 : 1;
-      slot[k2] += b ? 1 : 0;
-    }
-
-  if (world_ok) {
-    if (valid) {
-      row[0] = (a.policy == CA_POLICY_LEARNING_GA3C || a.policy == CA_POLICY_LEARNING) ? 1.f : 0.f;
-      row[1] = (float)count;
-      row[2] = (float)e.dist;
-      row[3] = e.hego;
-      row[4] = (float)a.ps;
-      row[5] = (float)a.rad;
-      for (int q = CA_OBS_HOST_LEN + CA_OBS_OTHER_LEN * count; q < p.L; ++q) row[q] = 0.f;
-      if (sidx_row) for (int k = count; k < M; ++k) sidx_row[k] = -1;
-    } else {
-      for (int q = 0; q < p.L; ++q) row[q] = 0.f;
-      if (sidx_row) for (int k = 0; k < M; ++k) sidx_row[k] = -1;
-    }
-  }
-  // second loop of the sensor (:105-144): every lane takes part in the velocity shuffles
-#pragma unroll
-  for (int k = 0; k < kN; ++k) {
-    const int j = k + (k >= i ? 1 : 0);
-    const int src = (base + j) & 31;
-    const double vxj = shfl_d(a.vx, src), vyj = shfl_d(a.vy, src);
-    if (valid && key[k] < INFINITY) {
-      float* s = row + CA_OBS_HOST_LEN + CA_OBS_OTHER_LEN * slot[k];
-      s[0] = (float)dot2(o.rx[k], o.ry[k], e.prx, e.pry);
-      s[1] = (float)o.po[k];
-      s[2] = (float)dot2(vxj, vyj, e.prx, e.pry);
-      s[3] = (float)dot2(vxj, vyj, -e.pry, e.prx);
-      s[4] = (float)o.rr[k];
-      s[5] = (float)(a.rad + o.rr[k]);
-      s[6] = (float)(o.d[k] - a.rad - o.rr[k]);
-      if (sidx_row) sidx_row[slot[k]] = j;
-    }
-  }
-}
 
 // Warp-level store of the warp's observation rows (its wpw worlds are contiguous in global memory).
 template <int kA>
