@@ -28,22 +28,47 @@ constexpr int kWarps = kBlock / 32;   // warps per CTA
 constexpr unsigned kFull = 0xffffffffu;
 constexpr double kPi = 3.141592653589793;  // np.pi
 
-struct StateArrays {
-  double *px, *py, *hd, *vx, *vy, *tr, *gx, *gy, *rad, *ps;  // [W*A] each
-  uint8_t *flags, *policy;                                     // [W*A]
+// ---- state layout in HBM: chunk-major AoSoA --------------------------------------------------------------------------
+// A "chunk" is what one warp processes: wpw = min(32 / A, 16) whole worlds = wpw * A (<= 32) agent slots, one per lane.
+// All state of a chunk lives in ONE contiguous, 128-byte aligned block of kBlkBytes = 2688 bytes:
+//     double field[kFields][32]      10 float64 fields x 32 lanes (px py heading vx vy time_remaining gx gy radius pref_speed)
+//     uint8  flags[32], policy[32]   per lane
+//     int32  num_agents[16]          per world of the chunk
+// so a warp reads/writes each field as one coalesced 256-byte run at a constant offset from a single base pointer, and
+// a chunk's entire state can be fetched with a single TMA bulk copy (ca_step_pipe.cuh).  The reset snapshot uses the
+// same layout in a second buffer.
+enum StateField { F_PX = 0, F_PY, F_HD, F_VX, F_VY, F_TR, F_GX, F_GY, F_RAD, F_PS, kFields };
+constexpr int kBlkDoubles = kFields * 32 + 16;  // 336 doubles
+constexpr int kBlkBytes = kBlkDoubles * 8;      // 2688 bytes
+
+struct StateBlocks {
+  double* base;  // [n_chunks][kBlkDoubles]
 };
 
+__host__ __device__ __forceinline__ int worlds_per_chunk(int A) { return (32 / A) < 16 ? (32 / A) : 16; }
+
+__device__ __forceinline__ double* blk_ptr(const StateBlocks& s, long chunk) { return s.base + chunk * kBlkDoubles; }
+__device__ __forceinline__ uint8_t* blk_flags(double* blk) { return reinterpret_cast<uint8_t*>(blk + kFields * 32); }
+__device__ __forceinline__ uint8_t* blk_policy(double* blk) { return reinterpret_cast<uint8_t*>(blk + kFields * 32) + 32; }
+__device__ __forceinline__ int32_t* blk_nag(double* blk) { return reinterpret_cast<int32_t*>(blk + kFields * 32 + 8); }
+
+// (world, agent) -> (chunk, lane) for kernels that are not organised warp-per-chunk
+__device__ __forceinline__ void slot_of(int w, int i, int A, long& chunk, int& lane, int& wl) {
+  const int wpw = worlds_per_chunk(A);
+  chunk = w / wpw;
+  wl = w - (int)chunk * wpw;
+  lane = wl * A + i;
+}
+
 struct Params {
-  int W, A, M, L, wpw;  // wpw = worlds per warp = 32 / A
+  int W, A, M, L, wpw;  // wpw = worlds per warp (chunk) = min(32 / A, 16)
   int sort_method, over_mode, auto_reset;
   int tile_floats;      // floats in the CTA's obs tile = kWarps * wpw * A * L
   int use_bulk_store;   // 1: TMA bulk store of full tiles
   int warp_store;       // specialised kernel: each warp stores its own rows (warp tile is a multiple of 16 B)
   double dt, thr_sq, close_range, r_goal, r_coll, r_step, r_min, r_max, max_heading_change, sensing_horizon;
-  StateArrays s;        // live state
-  StateArrays s0;       // snapshot injected by ca_set_world_state (for reset)
-  int32_t* nag;         // [W] live agent count per world
-  const int32_t* nag0;  // [W] agent count of the reset snapshot (a world may come back with a different count)
+  StateBlocks s;        // live state (agent counts inside the blocks)
+  StateBlocks s0;       // snapshot injected by ca_set_world_state / ca_set_reset_state / the generator (for reset)
   uint8_t* consumed;    // [W] set to 1 when a world takes its snapshot (the scenario generator refills those)
   // I/O (device)
   const int32_t* actions;  // [W*A]
@@ -189,10 +214,22 @@ struct Agent {
   int policy;
 };
 
-__device__ __forceinline__ void load_agent(const StateArrays& s, size_t g, Agent& a) {
-  a.px = s.px[g]; a.py = s.py[g]; a.hd = s.hd[g]; a.vx = s.vx[g]; a.vy = s.vy[g]; a.tr = s.tr[g];
-  a.gx = s.gx[g]; a.gy = s.gy[g]; a.rad = s.rad[g]; a.ps = s.ps[g];
-  a.flags = s.flags[g]; a.policy = s.policy[g];
+__device__ __forceinline__ void load_agent(const double* blk, int lane, Agent& a) {
+  a.px = blk[F_PX * 32 + lane]; a.py = blk[F_PY * 32 + lane]; a.hd = blk[F_HD * 32 + lane];
+  a.vx = blk[F_VX * 32 + lane]; a.vy = blk[F_VY * 32 + lane]; a.tr = blk[F_TR * 32 + lane];
+  a.gx = blk[F_GX * 32 + lane]; a.gy = blk[F_GY * 32 + lane]; a.rad = blk[F_RAD * 32 + lane];
+  a.ps = blk[F_PS * 32 + lane];
+  a.flags = blk_flags(const_cast<double*>(blk))[lane];
+  a.policy = blk_policy(const_cast<double*>(blk))[lane];
+}
+
+// write-back of one lane: the dynamic fields always, goal / static fields only when they changed
+__device__ __forceinline__ void store_agent(double* blk, int lane, const Agent& a, bool goal_too, bool all) {
+  blk[F_PX * 32 + lane] = a.px; blk[F_PY * 32 + lane] = a.py; blk[F_HD * 32 + lane] = a.hd;
+  blk[F_VX * 32 + lane] = a.vx; blk[F_VY * 32 + lane] = a.vy; blk[F_TR * 32 + lane] = a.tr;
+  blk_flags(blk)[lane] = (uint8_t)a.flags;
+  if (goal_too || all) { blk[F_GX * 32 + lane] = a.gx; blk[F_GY * 32 + lane] = a.gy; }
+  if (all) { blk[F_RAD * 32 + lane] = a.rad; blk[F_PS * 32 + lane] = a.ps; blk_policy(blk)[lane] = (uint8_t)a.policy; }
 }
 
 __device__ __forceinline__ void zero_agent(Agent& a) {
@@ -365,9 +402,12 @@ __global__ void __launch_bounds__(kBlock) ca_world_kernel(const __grid_constant_
   const long first_world_cta = (long)blockIdx.x * kWarps * p.wpw;
   const long w = first_world_cta + (long)warp * p.wpw + wl;
   const bool world_ok = wl < p.wpw && w < p.W;
+  const long chunk = (long)blockIdx.x * kWarps + warp;
+  double* const blk = blk_ptr(p.s, chunk);
+  double* const blk0 = blk_ptr(p.s0, chunk);
   pdl_wait();
   pdl_launch_dependents();
-  int n = world_ok ? p.nag[w] : 0;
+  int n = world_ok ? blk_nag(blk)[wl] : 0;
   bool valid = world_ok && i < n;
   const size_t g = world_ok ? (size_t)w * A + i : 0;
   const unsigned gmask = (A >= 32 ? kFull : ((1u << A) - 1u)) << (base & 31);
@@ -376,7 +416,7 @@ __global__ void __launch_bounds__(kBlock) ca_world_kernel(const __grid_constant_
   int32_t* sidx_row = (p.sidx && world_ok) ? p.sidx + g * p.M : nullptr;
 
   Agent a;
-  if (valid) load_agent(p.s, g, a); else zero_agent(a);
+  if (valid) load_agent(blk, lane, a); else zero_agent(a);
 
   bool do_reset;  // world reloads its injected initial state
   if (kStep) {
@@ -481,10 +521,10 @@ __global__ void __launch_bounds__(kBlock) ca_world_kernel(const __grid_constant_
   if (!kStep || __any_sync(kFull, do_reset)) {
     const bool again = kStep ? do_reset : true;  // this lane (re)computes its observation
     if (do_reset) {
-      n = p.nag0[w];
+      n = blk_nag(blk0)[wl];
       valid = i < n;
-      if (i == 0) { p.nag[w] = n; p.consumed[w] = 1; }
-      if (valid) load_agent(p.s0, g, a); else zero_agent(a);
+      if (i == 0) { blk_nag(blk)[wl] = n; p.consumed[w] = 1; }
+      if (valid) load_agent(blk0, lane, a); else zero_agent(a);
       e = ego_frame(a.px, a.py, a.gx, a.gy, a.hd);
     }
     bool c_unused;
@@ -494,13 +534,8 @@ __global__ void __launch_bounds__(kBlock) ca_world_kernel(const __grid_constant_
   }
 
   // ---- state write-back (coalesced; goal only changes for static agents / on reset)
-  if ((valid && kStep) || do_reset) {  // a reset rewrites every slot of the world (the scenario may have changed)
-    StateArrays s = p.s;
-    s.px[g] = a.px; s.py[g] = a.py; s.hd[g] = a.hd; s.vx[g] = a.vx; s.vy[g] = a.vy; s.tr[g] = a.tr;
-    s.flags[g] = (uint8_t)a.flags;
-    if (do_reset || a.policy == CA_POLICY_STATIC) { s.gx[g] = a.gx; s.gy[g] = a.gy; }
-    if (do_reset) { s.rad[g] = a.rad; s.ps[g] = a.ps; s.policy[g] = (uint8_t)a.policy; }
-  }
+  if ((valid && kStep) || do_reset)  // a reset rewrites every slot of the world (the scenario may have changed)
+    store_agent(blk, lane, a, a.policy == CA_POLICY_STATIC, do_reset);
 
   store_tile(p, sm.tile, first_world_cta, tid);
 }

@@ -21,8 +21,7 @@ namespace ca {
 
 struct ScenarioParams {
   ca_scenario_config c;
-  StateArrays s0;
-  int32_t* nag0;
+  StateBlocks s0;
   uint8_t* consumed;  // [W] set by the step kernels when a world resets; nullptr = regenerate every world
   int W, A;
   int only_consumed;
@@ -183,21 +182,25 @@ __global__ void __launch_bounds__(128) generate_scenarios_kernel(const ScenarioP
   }
   if (c.ensure_learner && !has_learner) pol[(int)(rng.u() * n) % n] = CA_POLICY_LEARNING_GA3C;
 
-  p.nag0[w] = n;
+  long chunk;
+  int lane0, wl;
+  slot_of(w, 0, A, chunk, lane0, wl);
+  double* blk = blk_ptr(p.s0, chunk);
+  blk_nag(blk)[wl] = n;
   for (int i = 0; i < A; ++i) {
-    const size_t g = (size_t)w * A + i;
+    const int lane = lane0 + i;
     const bool live = i < n;
     double t0 = 0.0;
     if (live) {
       t0 = p.max_time_ratio * ((norm2d(px[i] - gx[i], py[i] - gy[i]) - p.thr) / sp[i]);
       if (!(t0 > p.dt)) t0 = p.dt;
     }
-    p.s0.px[g] = live ? px[i] : 0.0; p.s0.py[g] = live ? py[i] : 0.0;
-    p.s0.gx[g] = live ? gx[i] : 0.0; p.s0.gy[g] = live ? gy[i] : 0.0;
-    p.s0.hd[g] = live ? (rng.u() * 2 * kPi - kPi) : 0.0;  // np.random.uniform(-pi, pi), test_cases.py:315
-    p.s0.vx[g] = 0.0; p.s0.vy[g] = 0.0; p.s0.tr[g] = t0;
-    p.s0.rad[g] = live ? rd[i] : 0.0; p.s0.ps[g] = live ? sp[i] : 0.0;
-    p.s0.flags[g] = 0; p.s0.policy[g] = live ? (uint8_t)pol[i] : 0;
+    blk[F_PX * 32 + lane] = live ? px[i] : 0.0; blk[F_PY * 32 + lane] = live ? py[i] : 0.0;
+    blk[F_GX * 32 + lane] = live ? gx[i] : 0.0; blk[F_GY * 32 + lane] = live ? gy[i] : 0.0;
+    blk[F_HD * 32 + lane] = live ? (rng.u() * 2 * kPi - kPi) : 0.0;  // np.random.uniform(-pi, pi), test_cases.py:315
+    blk[F_VX * 32 + lane] = 0.0; blk[F_VY * 32 + lane] = 0.0; blk[F_TR * 32 + lane] = t0;
+    blk[F_RAD * 32 + lane] = live ? rd[i] : 0.0; blk[F_PS * 32 + lane] = live ? sp[i] : 0.0;
+    blk_flags(blk)[lane] = 0; blk_policy(blk)[lane] = live ? (uint8_t)pol[i] : 0;
   }
 }
 

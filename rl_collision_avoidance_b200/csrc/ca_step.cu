@@ -67,12 +67,11 @@ struct ca_env {
   int pipe_grid = 0;
   size_t smem_pipe = 0;
   size_t smem_fast = 0;        // dynamic shared memory of the specialised step kernel (observation tile only)
-  double* slab = nullptr;      // 20 double arrays of W*A: live state then snapshot
-  uint8_t* bytes = nullptr;    // 4 uint8 arrays of W*A: flags, policy, flags0, policy0
-  int32_t* nag = nullptr;      // [2][W]: live agent counts, then the snapshot's
+  double* slab = nullptr;      // [2][n_chunks][kBlkDoubles]: live state blocks, then the reset snapshot (ca_kernels.cuh)
+  long n_chunks = 0;
   uint8_t* consumed = nullptr; // [W]: world took its snapshot since the last ca_generate_scenarios
   uint64_t gen_calls = 0;
-  ca::StateArrays s{}, s0{};
+  ca::StateBlocks s{}, s0{};
   bool initialised = false;
   int64_t launches = 0;
   // staging for the *_host entry points (lazily allocated)
@@ -92,19 +91,24 @@ namespace {
 using ca::kBlock;
 using ca::kWarps;
 
-// init[W][A][CA_INIT_STRIDE] (AoS, float64) -> SoA snapshot + live state.  Agent.__init__/reset, agent.py:29-136.
-__global__ void unpack_init_kernel(const double* __restrict__ init, const int32_t* __restrict__ nag_in,
-                                   int32_t* __restrict__ nag, int32_t* __restrict__ nag0, ca::StateArrays s,
-                                   ca::StateArrays s0, int W, int A, double max_time_ratio, double thr, double dt,
+// init[W][A][CA_INIT_STRIDE] (AoS, float64) -> chunk blocks of the snapshot (+ live state).  Agent.__init__/reset,
+// agent.py:29-136.
+__global__ void unpack_init_kernel(const double* __restrict__ init, const int32_t* __restrict__ nag_in, ca::StateBlocks s,
+                                   ca::StateBlocks s0, int W, int A, double max_time_ratio, double thr, double dt,
                                    bool snapshot_only) {
   const long g = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (g >= (long)W * A) return;
   const int w = (int)(g / A), i = (int)(g - (long)w * A);
   int n = nag_in[w];
   n = n < 1 ? 1 : (n > A ? A : n);
+  long chunk;
+  int lane, wl;
+  ca::slot_of(w, i, A, chunk, lane, wl);
+  double* b0 = ca::blk_ptr(s0, chunk);
+  double* b = ca::blk_ptr(s, chunk);
   if (i == 0) {
-    nag0[w] = n;
-    if (!snapshot_only) nag[w] = n;
+    ca::blk_nag(b0)[wl] = n;
+    if (!snapshot_only) ca::blk_nag(b)[wl] = n;
   }
   double v[CA_INIT_STRIDE];
 #pragma unroll
@@ -116,39 +120,32 @@ __global__ void unpack_init_kernel(const double* __restrict__ init, const int32_
     t0 = max_time_ratio * ((nrm - thr) / v[CA_I_PREF_SPEED]);
     if (!(t0 > dt)) t0 = dt;
   }
-  const double tr = i < n ? t0 : 0.0;
-  s0.px[g] = v[CA_I_PX]; s0.py[g] = v[CA_I_PY]; s0.hd[g] = v[CA_I_HEADING]; s0.vx[g] = 0.0; s0.vy[g] = 0.0; s0.tr[g] = tr;
-  s0.gx[g] = v[CA_I_GX]; s0.gy[g] = v[CA_I_GY]; s0.rad[g] = v[CA_I_RADIUS]; s0.ps[g] = v[CA_I_PREF_SPEED];
-  s0.flags[g] = 0; s0.policy[g] = (uint8_t)(int)v[CA_I_POLICY];
-  if (snapshot_only) return;
-  s.px[g] = v[CA_I_PX]; s.py[g] = v[CA_I_PY]; s.hd[g] = v[CA_I_HEADING]; s.vx[g] = 0.0; s.vy[g] = 0.0; s.tr[g] = tr;
-  s.gx[g] = v[CA_I_GX]; s.gy[g] = v[CA_I_GY]; s.rad[g] = v[CA_I_RADIUS]; s.ps[g] = v[CA_I_PREF_SPEED];
-  s.flags[g] = 0; s.policy[g] = (uint8_t)(int)v[CA_I_POLICY];
+  ca::Agent a;
+  a.px = v[CA_I_PX]; a.py = v[CA_I_PY]; a.hd = v[CA_I_HEADING]; a.vx = 0.0; a.vy = 0.0; a.tr = i < n ? t0 : 0.0;
+  a.gx = v[CA_I_GX]; a.gy = v[CA_I_GY]; a.rad = v[CA_I_RADIUS]; a.ps = v[CA_I_PREF_SPEED];
+  a.flags = 0; a.policy = (int)v[CA_I_POLICY];
+  ca::store_agent(b0, lane, a, true, true);
+  if (!snapshot_only) ca::store_agent(b, lane, a, true, true);
 }
 
-__global__ void pack_state_kernel(ca::StateArrays s, double* __restrict__ out, long total) {
+__global__ void pack_state_kernel(ca::StateBlocks s, double* __restrict__ out, int W, int A) {
   const long g = (long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (g >= total) return;
+  if (g >= (long)W * A) return;
+  const int w = (int)(g / A), i = (int)(g - (long)w * A);
+  long chunk;
+  int lane, wl;
+  ca::slot_of(w, i, A, chunk, lane, wl);
+  ca::Agent a;
+  ca::load_agent(ca::blk_ptr(s, chunk), lane, a);
   double* r = out + g * CA_STATE_STRIDE;
-  r[CA_S_PX] = s.px[g]; r[CA_S_PY] = s.py[g]; r[CA_S_HEADING] = s.hd[g]; r[CA_S_VX] = s.vx[g]; r[CA_S_VY] = s.vy[g];
-  r[CA_S_TIME_REMAINING] = s.tr[g]; r[CA_S_GX] = s.gx[g]; r[CA_S_GY] = s.gy[g]; r[CA_S_RADIUS] = s.rad[g];
-  r[CA_S_PREF_SPEED] = s.ps[g]; r[CA_S_FLAGS] = (double)s.flags[g]; r[CA_S_POLICY] = (double)s.policy[g];
+  r[CA_S_PX] = a.px; r[CA_S_PY] = a.py; r[CA_S_HEADING] = a.hd; r[CA_S_VX] = a.vx; r[CA_S_VY] = a.vy;
+  r[CA_S_TIME_REMAINING] = a.tr; r[CA_S_GX] = a.gx; r[CA_S_GY] = a.gy; r[CA_S_RADIUS] = a.rad;
+  r[CA_S_PREF_SPEED] = a.ps; r[CA_S_FLAGS] = (double)a.flags; r[CA_S_POLICY] = (double)a.policy;
 }
-
-// Array stride: W*A rounded up to 32 elements so that every SoA array starts 256-byte aligned (TMA bulk copies
-// need 16-byte aligned sources).
-size_t array_stride(const ca_env* e) { return (((size_t)e->W * e->A) + 31) & ~(size_t)31; }
 
 void carve(ca_env* e) {
-  const size_t n = array_stride(e);
-  double* d = e->slab;
-  ca::StateArrays* arr[2] = {&e->s, &e->s0};
-  for (int k = 0; k < 2; ++k) {
-    ca::StateArrays* s = arr[k];
-    s->px = d; d += n; s->py = d; d += n; s->hd = d; d += n; s->vx = d; d += n; s->vy = d; d += n;
-    s->tr = d; d += n; s->gx = d; d += n; s->gy = d; d += n; s->rad = d; d += n; s->ps = d; d += n;
-  }
-  e->s.flags = e->bytes; e->s.policy = e->bytes + n; e->s0.flags = e->bytes + 2 * n; e->s0.policy = e->bytes + 3 * n;
+  e->s.base = e->slab;
+  e->s0.base = e->slab + (size_t)e->n_chunks * ca::kBlkDoubles;
 }
 
 ca::Params make_params(const ca_env* e) {
@@ -165,7 +162,7 @@ ca::Params make_params(const ca_env* e) {
   p.r_min = c.min_possible_reward; p.r_max = c.max_possible_reward;
   p.max_heading_change = c.max_heading_change;
   p.sensing_horizon = c.sensing_horizon;
-  p.s = e->s; p.s0 = e->s0; p.nag = e->nag; p.nag0 = e->nag + e->W; p.consumed = e->consumed;
+  p.s = e->s; p.s0 = e->s0; p.consumed = e->consumed;
   return p;
 }
 
@@ -380,7 +377,8 @@ int ca_create(const ca_config* cfg, ca_env** out) {
   e->cfg = *cfg;
   e->W = cfg->num_worlds; e->A = cfg->max_agents; e->M = cfg->max_others_observed;
   e->L = CA_OBS_LEN(e->M);
-  e->wpw = 32 / e->A;
+  e->wpw = ca::worlds_per_chunk(e->A);
+  e->n_chunks = ((long)e->W + e->wpw - 1) / e->wpw;
   const int worlds_per_cta = kWarps * e->wpw;
   e->grid = (e->W + worlds_per_cta - 1) / worlds_per_cta;
   e->tile_floats = worlds_per_cta * e->A * e->L;
@@ -436,16 +434,14 @@ int ca_create(const ca_config* cfg, ca_env** out) {
     delete e;
     return fail(CA_ERR_CUDA, "kernel image not usable on this device (built for sm_100a): %s", cudaGetErrorString(ce));
   }
-  const size_t n = (size_t)e->W * e->A;
-  const size_t ns = array_stride(e);
-  if (cudaMalloc(&e->slab, ns * 20 * sizeof(double)) != cudaSuccess || cudaMalloc(&e->bytes, ns * 4) != cudaSuccess ||
-      cudaMalloc(&e->nag, (size_t)e->W * 2 * sizeof(int32_t)) != cudaSuccess ||
-      cudaMalloc(&e->consumed, (size_t)e->W) != cudaSuccess) {
-    cudaFree(e->slab); cudaFree(e->bytes); cudaFree(e->nag); cudaFree(e->consumed);
+  const size_t slab_bytes = (size_t)e->n_chunks * ca::kBlkBytes * 2;
+  if (cudaMalloc(&e->slab, slab_bytes) != cudaSuccess || cudaMalloc(&e->consumed, (size_t)e->W) != cudaSuccess) {
+    cudaFree(e->slab); cudaFree(e->consumed);
     delete e;
     cudaGetLastError();
-    return fail(CA_ERR_ALLOC, "cudaMalloc of %zu state bytes failed", n * 20 * sizeof(double));
+    return fail(CA_ERR_ALLOC, "cudaMalloc of %zu state bytes failed", slab_bytes);
   }
+  cudaMemset(e->slab, 0, slab_bytes);
   carve(e);
   cudaMemset(e->consumed, 0, (size_t)e->W);
   *out = e;
@@ -456,7 +452,7 @@ int ca_destroy(ca_env* e) {
   if (!e) return CA_OK;
   DeviceGuard guard(e->cfg.device);
   cudaDeviceSynchronize();
-  cudaFree(e->slab); cudaFree(e->bytes); cudaFree(e->nag); cudaFree(e->consumed);
+  cudaFree(e->slab); cudaFree(e->consumed);
   cudaFree(e->d_actions); cudaFree(e->d_cont); cudaFree(e->d_obs); cudaFree(e->d_reward);
   cudaFree(e->d_done); cudaFree(e->d_over); cudaFree(e->d_mask); cudaFree(e->d_sidx);
   if (e->hstream) cudaStreamDestroy(e->hstream);
@@ -487,8 +483,8 @@ static int set_state_impl(ca_env* e, const double* init, const int32_t* num_agen
   }
   const int threads = 256;
   const int blocks = (int)((n + threads - 1) / threads);
-  unpack_init_kernel<<<blocks, threads, 0, st>>>(d_init, d_nag, e->nag, e->nag + e->W, e->s, e->s0, e->W, e->A,
-                                                 e->cfg.max_time_ratio, e->cfg.near_goal_threshold, e->cfg.dt, snapshot_only);
+  unpack_init_kernel<<<blocks, threads, 0, st>>>(d_init, d_nag, e->s, e->s0, e->W, e->A, e->cfg.max_time_ratio,
+                                                 e->cfg.near_goal_threshold, e->cfg.dt, snapshot_only);
   CA_CUDA(cudaPeekAtLastError());
   e->launches += 1;
   if (!on_device) {
@@ -582,7 +578,7 @@ int ca_get_state(ca_env* e, double* out, int on_device, void* stream) {
   double* d_out = out;
   if (!on_device) CA_CUDA(cudaMalloc(&d_out, n * CA_STATE_STRIDE * sizeof(double)));
   const int threads = 256;
-  pack_state_kernel<<<(int)((n + threads - 1) / threads), threads, 0, st>>>(e->s, d_out, (long)n);
+  pack_state_kernel<<<(int)((n + threads - 1) / threads), threads, 0, st>>>(e->s, d_out, e->W, e->A);
   CA_CUDA(cudaPeekAtLastError());
   e->launches += 1;
   if (!on_device) {
@@ -647,7 +643,7 @@ int ca_generate_scenarios(ca_env* e, const ca_scenario_config* c, uint64_t seed,
   DeviceGuard guard(e->cfg.device);
   ca::ScenarioParams p;
   memset(&p, 0, sizeof(p));
-  p.c = *c; p.s0 = e->s0; p.nag0 = e->nag + e->W; p.consumed = e->consumed; p.W = e->W; p.A = e->A;
+  p.c = *c; p.s0 = e->s0; p.consumed = e->consumed; p.W = e->W; p.A = e->A;
   p.only_consumed = only_consumed; p.dt = e->cfg.dt; p.thr = e->cfg.near_goal_threshold;
   p.max_time_ratio = e->cfg.max_time_ratio; p.seed = seed; p.offset = e->gen_calls * 4096ull;
   e->gen_calls += 1;
@@ -658,9 +654,7 @@ int ca_generate_scenarios(ca_env* e, const ca_scenario_config* c, uint64_t seed,
   if (!e->initialised && !only_consumed) {
     // first use without ca_set_world_state: the generated snapshot defines the worlds; the caller must ca_reset (all
     // worlds) before stepping.  Live worlds of an initialised handle are never touched by the generator.
-    CA_CUDA(cudaMemcpyAsync(e->nag, e->nag + e->W, (size_t)e->W * sizeof(int32_t), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
-    CA_CUDA(cudaMemsetAsync(e->slab, 0, array_stride(e) * 10 * sizeof(double), (cudaStream_t)stream));
-    CA_CUDA(cudaMemsetAsync(e->bytes, 0, array_stride(e) * 2, (cudaStream_t)stream));
+    // (live blocks are all zero from ca_create: agent count 0 everywhere until the reset adopts the snapshot)
     e->initialised = true;
   }
   return CA_OK;

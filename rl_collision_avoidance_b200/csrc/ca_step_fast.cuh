@@ -19,7 +19,7 @@ namespace ca {
 template <int kA>
 __device__ __forceinline__ void fast_store_warp_tile(const Params& p, const float* wtile, long first_world_warp,
                                                      int lane) {
-  constexpr int wpw = 32 / kA;
+  constexpr int wpw = (32 / kA) < 16 ? (32 / kA) : 16;
   const long worlds_left = (long)p.W - first_world_warp;
   if (worlds_left <= 0) return;
   const int nw = worlds_left < wpw ? (int)worlds_left : wpw;
@@ -50,7 +50,7 @@ __device__ __forceinline__ void fast_store_warp_tile(const Params& p, const floa
 template <int kA, int kMinBlocks, bool kDbg>
 __global__ void __launch_bounds__(kBlock, kMinBlocks) ca_step_kernel(const __grid_constant__ Params p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  constexpr int wpw = 32 / kA;
+  constexpr int wpw = (32 / kA) < 16 ? (32 / kA) : 16;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int wl = lane / kA;
   const int i = lane - wl * kA;
@@ -59,9 +59,11 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks) ca_step_kernel(const __gri
   const long w = first_world_warp + wl;
   const bool world_ok = wl < wpw && w < p.W;
   const size_t g = world_ok ? (size_t)w * kA + i : 0;
+  const long chunk = (long)blockIdx.x * kWarps + warp;
+  double* const blk = blk_ptr(p.s, chunk);
   pdl_wait();                // nothing produced by the previous kernel is read above this line
   pdl_launch_dependents();
-  int n = world_ok ? p.nag[w] : 0;
+  int n = world_ok ? blk_nag(blk)[wl] : 0;
   bool valid = world_ok && i < n;
   const unsigned gmask = (kA >= 32 ? kFull : ((1u << kA) - 1u)) << (base & 31);
 
@@ -76,7 +78,7 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks) ca_step_kernel(const __gri
   Agent a;
   int act = 0;
   if (world_ok) {
-    load_agent(p.s, g, a);
+    load_agent(blk, lane, a);
     act = p.actions[g];
   }
   if (!valid) { zero_agent(a); act = 0; }
@@ -174,10 +176,11 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks) ca_step_kernel(const __gri
     // DummyVecEnv semantics: worlds that finished reload their injected initial state and observe again;
     // the other worlds of the warp observe their post-step state.
     if (do_reset) {
-      n = p.nag0[w];
+      double* const blk0 = blk_ptr(p.s0, chunk);
+      n = blk_nag(blk0)[wl];
       valid = i < n;
-      if (i == 0) { p.nag[w] = n; p.consumed[w] = 1; }
-      if (valid) load_agent(p.s0, g, a); else zero_agent(a);
+      if (i == 0) { blk_nag(blk)[wl] = n; p.consumed[w] = 1; }
+      if (valid) load_agent(blk0, lane, a); else zero_agent(a);
       e = ego_frame(a.px, a.py, a.gx, a.gy, a.hd);
     }
     bool c_unused;
@@ -187,13 +190,8 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks) ca_step_kernel(const __gri
   }
 
   // ---- state write-back
-  if (valid || do_reset) {  // a reset rewrites every slot of the world (the new scenario may have fewer agents)
-    StateArrays s = p.s;
-    s.px[g] = a.px; s.py[g] = a.py; s.hd[g] = a.hd; s.vx[g] = a.vx; s.vy[g] = a.vy; s.tr[g] = a.tr;
-    s.flags[g] = (uint8_t)a.flags;
-    if (do_reset || a.policy == CA_POLICY_STATIC) { s.gx[g] = a.gx; s.gy[g] = a.gy; }
-    if (do_reset) { s.rad[g] = a.rad; s.ps[g] = a.ps; s.policy[g] = (uint8_t)a.policy; }
-  }
+  if (valid || do_reset)  // a reset rewrites every slot of the world (the new scenario may have fewer agents)
+    store_agent(blk, lane, a, a.policy == CA_POLICY_STATIC, do_reset);
 
   if (p.warp_store) fast_store_warp_tile<kA>(p, wtile, first_world_warp, lane);
   else store_tile(p, reinterpret_cast<float*>(smem_raw), (long)blockIdx.x * kWarps * wpw, tid);

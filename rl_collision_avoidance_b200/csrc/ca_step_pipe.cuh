@@ -45,8 +45,7 @@ __device__ __forceinline__ void tma_load_1d(void* dst_smem, const void* src_gmem
                : "memory");
 }
 
-constexpr int kStateArrays = 10;                      // px py hd vx vy tr gx gy rad ps
-constexpr int kStageBytes = kStateArrays * 32 * 8;    // one warp's state stage
+constexpr int kStageBytes = kBlkBytes;                // one warp's state stage = one chunk block (2688 B)
 
 template <int kA>
 struct OthersLite {
@@ -175,7 +174,7 @@ __device__ __forceinline__ void pipe_write_obs_row(const Params& p, const Agent&
 template <int kA, int kMinBlocks, bool kDbg>
 __global__ void __launch_bounds__(kBlock, kMinBlocks) ca_step_pipe_kernel(const __grid_constant__ Params p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  constexpr int wpw = 32 / kA;
+  constexpr int wpw = (32 / kA) < 16 ? (32 / kA) : 16;
   constexpr int kLanesUsed = wpw * kA;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int wl = lane / kA;
@@ -205,25 +204,16 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks) ca_step_pipe_kernel(const 
   }
   __syncwarp();
 
-  const double* src_arrays[kStateArrays] = {p.s.px, p.s.py, p.s.hd, p.s.vx, p.s.vy, p.s.tr, p.s.gx, p.s.gy, p.s.rad, p.s.ps};
-
-  // issue the loads of chunk c: TMA for the float64 arrays (full chunks only), registers for the small ones
-  int pf_n = 0, pf_act = 0;
-  unsigned pf_flags = 0, pf_policy = 0;
+  // issue the loads of chunk c: ONE TMA bulk copy brings the chunk's whole state block (10 float64 fields, flags,
+  // policies, agent counts) into the warp's stage; only the caller's action array is prefetched into a register
+  int pf_act = 0;
   auto prefetch = [&](long c) {
     const long w = c * wpw + wl;
     const bool ok = lane_used && w < p.W;
-    const size_t g = ok ? (size_t)w * kA + i : 0;
-    pf_n = ok ? p.nag[w] : 0;
-    pf_act = ok ? p.actions[g] : 0;
-    pf_flags = ok ? p.s.flags[g] : 0;
-    pf_policy = ok ? p.s.policy[g] : 0;
-    const bool full = (c + 1) * wpw <= p.W;
-    if (full && lane == 0) {
-      mbar_arrive_expect_tx(bar, kStateArrays * kLanesUsed * 8);
-      const size_t g0 = (size_t)c * kLanesUsed;
-#pragma unroll
-      for (int k = 0; k < kStateArrays; ++k) tma_load_1d(stage + k * 32, src_arrays[k] + g0, kLanesUsed * 8, bar);
+    pf_act = ok ? p.actions[(size_t)w * kA + i] : 0;
+    if (lane == 0) {
+      mbar_arrive_expect_tx(bar, kBlkBytes);
+      tma_load_1d(stage, blk_ptr(p.s, c), kBlkBytes, bar);
     }
   };
 
@@ -239,27 +229,16 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks) ca_step_pipe_kernel(const 
     const bool world_ok = lane_used && w < p.W;
     const size_t g = world_ok ? (size_t)w * kA + i : 0;
     const bool full = (c + 1) * wpw <= p.W;
-    int n = pf_n;
-    bool valid = world_ok && i < n;
+    double* const blk = blk_ptr(p.s, c);
     int32_t* sidx_row = (p.sidx && world_ok) ? p.sidx + g * p.M : nullptr;
 
+    // the chunk's block has landed in the stage (padded blocks make partial last chunks loadable too)
+    mbar_wait(bar, parity);
+    parity ^= 1u;
+    int n = world_ok ? blk_nag(stage)[wl] : 0;
+    bool valid = world_ok && i < n;
     Agent a;
-    if (full) {
-      mbar_wait(bar, parity);
-      parity ^= 1u;
-      if (valid) {
-        a.px = stage[0 * 32 + lane]; a.py = stage[1 * 32 + lane]; a.hd = stage[2 * 32 + lane];
-        a.vx = stage[3 * 32 + lane]; a.vy = stage[4 * 32 + lane]; a.tr = stage[5 * 32 + lane];
-        a.gx = stage[6 * 32 + lane]; a.gy = stage[7 * 32 + lane]; a.rad = stage[8 * 32 + lane];
-        a.ps = stage[9 * 32 + lane];
-      } else {
-        zero_agent(a);
-      }
-    } else {
-      if (valid) load_agent(p.s, g, a); else zero_agent(a);
-    }
-    a.flags = valid ? pf_flags : 0;
-    a.policy = valid ? (int)pf_policy : 0;
+    if (valid) load_agent(stage, lane, a); else zero_agent(a);
     const int act = pf_act;
     __syncwarp();  // every lane has copied its state out of the stage: it may be refilled
     if (c + GW < n_chunks) prefetch(c + GW);
@@ -353,10 +332,11 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks) ca_step_pipe_kernel(const 
 
     if (__any_sync(kFull, do_reset)) {
       if (do_reset) {
-        n = p.nag0[w];
+        double* const blk0 = blk_ptr(p.s0, c);
+        n = blk_nag(blk0)[wl];
         valid = i < n;
-        if (i == 0) { p.nag[w] = n; p.consumed[w] = 1; }
-        if (valid) load_agent(p.s0, g, a); else zero_agent(a);
+        if (i == 0) { blk_nag(blk)[wl] = n; p.consumed[w] = 1; }
+        if (valid) load_agent(blk0, lane, a); else zero_agent(a);
         e = ego_frame(a.px, a.py, a.gx, a.gy, a.hd);
       }
       bool c_unused;
@@ -373,13 +353,7 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks) ca_step_pipe_kernel(const 
     pipe_write_obs_row<kA, kDbg>(p, a, e, world_ok, valid, i, base, o, row, sidx_row);
 
     // ---- state write-back (coalesced)
-    if (valid || do_reset) {
-      StateArrays s = p.s;
-      s.px[g] = a.px; s.py[g] = a.py; s.hd[g] = a.hd; s.vx[g] = a.vx; s.vy[g] = a.vy; s.tr[g] = a.tr;
-      s.flags[g] = (uint8_t)a.flags;
-      if (do_reset || a.policy == CA_POLICY_STATIC) { s.gx[g] = a.gx; s.gy[g] = a.gy; }
-      if (do_reset) { s.rad[g] = a.rad; s.ps[g] = a.ps; s.policy[g] = (uint8_t)a.policy; }
-    }
+    if (valid || do_reset) store_agent(blk, lane, a, a.policy == CA_POLICY_STATIC, do_reset);
 
     // ---- observation tile -> global
     float* dst = p.obs + (size_t)first_world * kA * p.L;
