@@ -230,7 +230,7 @@ def run_ours(args):
     gen = torch.Generator(device="cuda")
     gen.manual_seed(1234 + rank)
     actions = [torch.randint(0, 11, (W, A), dtype=torch.int32, device="cuda", generator=gen) for _ in range(T)]
-    bytes_per_set = W * A * (20 * 8 + 4) + W * A * _abi.obs_len(OTHERS) * 4 + W * A * 9
+    bytes_per_set = 2 * (W // 8) * 2688 + W * A * 4 + W * A * _abi.obs_len(OTHERS) * 4 + W * A * 9   # state blocks x2, actions, obs, outputs
 
     def eager_step(k):
         envs[k % R].step(actions[k % T])
@@ -321,7 +321,7 @@ def run_ours(args):
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": ncu_traffic_per_launch(), "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": ALG_BYTES_PER_AGENT_STEP * W * A,
-                         "kernel": "ca::ca_step_kernel<4>", "launch_ms": launch_ms},
+                         "kernel": "ca::ca_step_kernel<4, 7, false>", "launch_ms": launch_ms},
         }
         if world_size == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline_run(args.cpu_seconds, 16384)

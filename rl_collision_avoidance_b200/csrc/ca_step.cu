@@ -185,7 +185,7 @@ bool has_fast_kernel(const ca_env* e) {
 cudaError_t set_fast_smem_attr(int A, int bytes);
 
 // Instantiations of the pipelined kernel: (agent slots, min CTAs per SM used for register allocation).
-#define CA_PIPE_VARIANTS(X) X(2, 6) X(3, 6) X(4, 5) X(4, 7) X(5, 5) X(6, 5) X(8, 4) X(10, 3)
+#define CA_PIPE_VARIANTS(X) X(2, 6) X(3, 6) X(4, 5) X(4, 6) X(4, 7) X(5, 5) X(6, 5) X(8, 4) X(10, 3)
 
 int default_pipe_min_blocks(int A) {
   switch (A) {
