@@ -66,6 +66,7 @@ struct Params {
   int tile_floats;      // floats in the CTA's obs tile = kWarps * wpw * A * L
   int use_bulk_store;   // 1: TMA bulk store of full tiles
   int warp_store;       // specialised kernel: each warp stores its own rows (warp tile is a multiple of 16 B)
+  int prefetch_chunks;  // one-shot kernel: L2-prefetch the state block of chunk + prefetch_chunks (0 = off)
   double dt, thr_sq, close_range, r_goal, r_coll, r_step, r_min, r_max, max_heading_change, sensing_horizon;
   StateBlocks s;        // live state (agent counts inside the blocks)
   StateBlocks s0;       // snapshot injected by ca_set_world_state / ca_set_reset_state / the generator (for reset)

@@ -66,6 +66,7 @@ struct ca_env {
   int pipe_min_blocks = 0;     // 0 = default instantiation
   int pipe_grid = 0;
   size_t smem_pipe = 0;
+  int prefetch_chunks = 0;     // resident warps of the one-shot kernel (= distance of its L2 prefetch), 0 = off
   size_t smem_fast = 0;        // dynamic shared memory of the specialised step kernel (observation tile only)
   double* slab = nullptr;      // [2][n_chunks][kBlkDoubles]: live state blocks, then the reset snapshot (ca_kernels.cuh)
   long n_chunks = 0;
@@ -275,6 +276,7 @@ int launch_world_kernel(ca_env* e, bool step, ca::Params& p, cudaStream_t st) {
     rc = launch_pdl(pipe_kernel_ptr(e->A, e->pipe_min_blocks, dbg), e->pipe_grid, e->smem_pipe, st, p, e->use_pdl);
   } else if (step && has_fast_kernel(e)) {
     if (e->store_vec4 && aligned16(p.obs) && p.warp_store) p.use_bulk_store = 2;
+    p.prefetch_chunks = e->prefetch_chunks;
     rc = launch_pdl(fast_kernel_ptr(e->A, dbg), e->grid, e->smem_fast, st, p, e->use_pdl);
   } else if (step) {
     rc = launch_pdl((const void*)ca::ca_world_kernel<true>, e->grid, e->smem_bytes, st, p, e->use_pdl);
@@ -401,6 +403,14 @@ int ca_create(const ca_config* cfg, ca_env** out) {
   if (ce == cudaSuccess)
     ce = cudaFuncSetAttribute(ca::ca_world_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem_bytes);
   if (ce == cudaSuccess) ce = set_fast_smem_attr(e->A, (int)e->smem_fast);
+  if (ce == cudaSuccess && has_fast_kernel(e)) {  // how many CTAs of the one-shot kernel are resident at once
+    int per_sm = 0, sms = 0;
+    ce = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fast_kernel_ptr(e->A, false), kBlock, e->smem_fast);
+    if (ce == cudaSuccess) ce = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, cfg->device);
+    const char* pf = getenv("CA_DISABLE_L2_PREFETCH");
+    if (ce == cudaSuccess && !(pf && pf[0] == '1') && (long)per_sm * sms < (long)e->grid)
+      e->prefetch_chunks = per_sm * sms * kWarps;
+  }
   const char* kc = getenv("CA_STEP_KERNEL");  // "oneshot" (default) | "pipe" | "generic"
   if (kc && strcmp(kc, "oneshot") == 0) e->kernel_choice = 1;
   if (kc && strcmp(kc, "pipe") == 0) e->kernel_choice = 0;

@@ -136,6 +136,17 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks) ca_step_kernel(const __gri
   double nearest;
   pipe_pair_pass<kA, true, kDbg>(p, a, e, valid, n, i, base, o, coll, nearest);
 
+  if (p.prefetch_chunks > 0 && lane == 0) {
+    // The grid runs in about two rounds of resident CTAs.  By now this round's own load burst has drained and DRAM is
+    // idle while the warps compute: pull the state block and the actions of the chunk that will run in this slot one
+    // round later into L2 (TMA bulk prefetch), so the second round does not start with another DRAM burst.
+    const long pc = chunk + p.prefetch_chunks;
+    if (pc * wpw < p.W) {
+      asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(blk_ptr(p.s, pc)), "r"(kBlkBytes) : "memory");
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(p.actions + (size_t)pc * wpw * kA) : "memory");
+    }
+  }
+
   // ---- _compute_rewards (:319-368)
   double r = p.r_step;
   if (valid) {
