@@ -91,7 +91,8 @@ class Train(EnvConfig):
 
         # ---- GPU-only knobs
         s.GPU_NUM_WORLDS = int(os.environ.get('GA3C_GPU_NUM_WORLDS', 4096))   # worlds stepped per launch on each GPU
-        s.GPU_TRAIN_BATCH = int(os.environ.get('GA3C_GPU_TRAIN_BATCH', 8192)) # rows per optimiser step (>= TRAINING_MIN_BATCH_SIZE)
+        # rows per optimiser step (>= TRAINING_MIN_BATCH_SIZE); 0 = auto: about one step per env step (max(8192, worlds * agents))
+        s.GPU_TRAIN_BATCH = int(os.environ.get('GA3C_GPU_TRAIN_BATCH', 0))
         s.GPU_PRINT_EVERY_S = 2.0
 
 

@@ -175,7 +175,8 @@ class Server(object):
 
     def _train_pending(self, force=False):
         cfg = self.cfg
-        batch = max(cfg.GPU_TRAIN_BATCH, cfg.TRAINING_MIN_BATCH_SIZE + 1)
+        auto = max(8192, self.num_worlds * cfg.MAX_NUM_AGENTS_IN_ENVIRONMENT)
+        batch = max(cfg.GPU_TRAIN_BATCH if cfg.GPU_TRAIN_BATCH > 0 else auto, cfg.TRAINING_MIN_BATCH_SIZE + 1)
         torch = self.torch
         if self.dist:
             return self._train_pending_distributed(batch, force)
