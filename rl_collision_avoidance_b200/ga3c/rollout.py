@@ -70,7 +70,9 @@ class ExperienceRecorder(object):
 
     def take(self):
         """Returns views (x_ [k, L-1], r_ [k], a_ [k]) of the rows emitted since the last take() and resets the counter.
-        Synchronises on the row count (one 4-byte D2H read)."""
+        Synchronises on the row count (one 4-byte D2H read).  Call it after every step (or at least before the rows of
+        several steps can exceed `capacity` = one step's worst case, N * (TIME_MAX + 1)); overflow raises instead of
+        silently dropping rows."""
         k = int(self.out_count.item())
         if k > self.capacity:
             raise RuntimeError("experience output overflow: %d rows emitted, capacity %d" % (k, self.capacity))

@@ -1,0 +1,49 @@
+"""Small workload for compute-sanitizer (memcheck / racecheck / synccheck): every kernel variant, ragged worlds,
+auto-reset with streamed scenarios, the generator, the GA3C bookkeeping and the fused LSTM step."""
+import os
+import sys
+
+import numpy as np
+import torch
+
+sys.path.insert(0, ".")
+from rl_collision_avoidance_b200 import _abi
+from rl_collision_avoidance_b200.vec_env import HostVecEnv, VecCollisionAvoidanceEnv
+from rl_collision_avoidance_b200.scenarios import random_worlds
+
+rng = np.random.default_rng(0)
+for kern in ("oneshot", "pipe", "generic"):
+    os.environ["CA_STEP_KERNEL"] = kern
+    for A, W in ((4, 531), (10, 77), (3, 100)):
+        init, nag = random_worlds(W, A, rng, num_agents=rng.integers(2, A + 1, W), policies=['noncoop', 'learning_ga3c', 'static'],
+                                  policy_distr=[0.2, 0.6, 0.2], policy_to_ensure='learning_ga3c')
+        env = HostVecEnv(_abi.default_config(W, A, auto_reset=1), want_sorted_idx=(kern != "oneshot"))
+        env.set_world_state(init, nag)
+        env.reset()
+        for t in range(12):
+            env.step(rng.integers(0, 11, (W, A)).astype(np.int32))
+        env.get_state()
+        env.close()
+    print(kern, "ok", flush=True)
+os.environ["CA_STEP_KERNEL"] = "oneshot"
+env = VecCollisionAvoidanceEnv(_abi.default_config(300, 4, auto_reset=1))
+sc = env.scenario_config({'policies': ['noncoop', 'learning_ga3c', 'static'], 'policy_distr': [0.05, 0.9, 0.05],
+                          'policy_to_ensure': 'learning_ga3c'})
+env.generate_scenarios(sc, 3)
+env.reset()
+for t in range(30):
+    env.step(torch.randint(0, 11, (300, 4), dtype=torch.int32, device="cuda"))
+    env.generate_scenarios(sc, 3, only_consumed=True)
+torch.cuda.synchronize()
+print("generator ok", flush=True)
+from rl_collision_avoidance_b200.ga3c import Config as cfgmod
+from rl_collision_avoidance_b200.ga3c.NetworkVP_rnn import NetworkVP_rnn
+from rl_collision_avoidance_b200.ga3c.rollout import GpuRollout
+cfg = cfgmod.TrainPhase1(); cfgmod.set_config(cfg)
+init, nag = random_worlds(64, 4, rng)
+ro = GpuRollout(cfg, NetworkVP_rnn("cuda:0", "network", 11), 64, init, nag)
+for t in range(30):
+    ro.step()
+    ro.rec.take()          # the recorder is drained every step (capacity = one step's worst case)
+torch.cuda.synchronize()
+print("rollout ok", flush=True)
