@@ -342,14 +342,17 @@ __device__ __forceinline__ void write_obs_row(const Params& p, const Smem& sm, c
       const int ak = k * kBlock + tid;
       slot += key_before(mode2, sm.kq[ak], sm.kp[ak], tti ? sm.kt[ak] : 0.0, k, qj, pj, tj, j) ? 1 : 0;
     }
-    const double rx = xj - a.px, ry = yj - a.py;
+    // observation-only projections are evaluated in float32 from the rounded float64 inputs (same formulas as
+    // pipe_write_obs_row, so that all step kernels agree bit for bit); p_orth is the float64 tie-break key
+    const float rxf = (float)(xj - a.px), ryf = (float)(yj - a.py), prxf = (float)e.prx, pryf = (float)e.pry;
+    const float vxf = (float)vxj, vyf = (float)vyj, rjf = (float)rj, raf = (float)a.rad;
     float* s = row + CA_OBS_HOST_LEN + CA_OBS_OTHER_LEN * slot;
-    s[0] = (float)dot2(rx, ry, e.prx, e.pry);
+    s[0] = fmaf(ryf, pryf, rxf * prxf);
     s[1] = (float)pj;
-    s[2] = (float)dot2(vxj, vyj, e.prx, e.pry);
-    s[3] = (float)dot2(vxj, vyj, -e.pry, e.prx);
-    s[4] = (float)rj;
-    s[5] = (float)(a.rad + rj);
+    s[2] = fmaf(vyf, pryf, vxf * prxf);
+    s[3] = fmaf(vyf, prxf, -(vxf * pryf));
+    s[4] = rjf;
+    s[5] = raf + rjf;
     s[6] = (float)(sm.kd[aj] - a.rad - rj);
     if (sidx_row) sidx_row[slot] = j;
   }

@@ -181,7 +181,10 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks) ca_step_kernel(const __gri
   }
   const bool do_reset = world_ok && over && p.auto_reset;
 
+  // The state is written back BEFORE the observation rows are assembled: heading, time budget, goal and flags die
+  // here instead of occupying registers through the ranking / row code.
   if (!__any_sync(kFull, do_reset)) {
+    if (valid) store_agent(blk, lane, a, a.policy == CA_POLICY_STATIC, false);
     pipe_write_obs_row<kA, kDbg>(p, a, e, world_ok, valid, i, base, o, row, sidx_row);
   } else {
     // DummyVecEnv semantics: worlds that finished reload their injected initial state and observe again;
@@ -194,15 +197,13 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks) ca_step_kernel(const __gri
       if (valid) load_agent(blk0, lane, a); else zero_agent(a);
       e = ego_frame(a.px, a.py, a.gx, a.gy, a.hd);
     }
+    if (valid || do_reset)  // a reset rewrites every slot of the world (the new scenario may have fewer agents)
+      store_agent(blk, lane, a, a.policy == CA_POLICY_STATIC, do_reset);
     bool c_unused;
     double n_unused;
     pipe_pair_pass<kA, false, kDbg>(p, a, e, valid, n, i, base, o, c_unused, n_unused);
     pipe_write_obs_row<kA, kDbg>(p, a, e, world_ok, valid, i, base, o, row, sidx_row);
   }
-
-  // ---- state write-back
-  if (valid || do_reset)  // a reset rewrites every slot of the world (the new scenario may have fewer agents)
-    store_agent(blk, lane, a, a.policy == CA_POLICY_STATIC, do_reset);
 
   if (p.warp_store) fast_store_warp_tile<kA>(p, wtile, first_world_warp, lane);
   else store_tile(p, reinterpret_cast<float*>(smem_raw), (long)blockIdx.x * kWarps * wpw, tid);

@@ -51,8 +51,10 @@ template <int kA>
 struct OthersLite {
   static constexpr int kN = kA > 1 ? kA - 1 : 1;
   int key[kN];      // rint(100 * dist_2_other); INT_MAX for an absent / unobserved other
-  double po[kN];    // p_orth
-  double d[kN];     // centre distance
+  double po[kN];    // p_orth (float64: it breaks ties between equal keys)
+  // observation-only copies (float32 outputs with 1e-5 tolerance, no decision reads them): relative position of the
+  // other, its radius and the boundary distance, so that the row assembly needs no second round of float64 shuffles
+  float rx[kN], ry[kN], rr[kN], d2o[kN];
 };
 
 // kDbg selects the rarely used features (finite SENSING_HORIZON, neighbour-index output for parity tests); the
@@ -77,9 +79,10 @@ __device__ __forceinline__ void pipe_pair_pass(const Params& p, const Agent& a, 
       if (j > i) nearest = fmin(nearest, d - R);
     }
     const bool seen = live && !(horizon && d > p.sensing_horizon);
-    o.key[k] = seen ? __double2int_rn((d - a.rad - rj) * 100.0) : INT_MAX;
+    const double d2o = d - a.rad - rj;
+    o.key[k] = seen ? __double2int_rn(d2o * 100.0) : INT_MAX;
     o.po[k] = dot2(rx, ry, -e.pry, e.prx);
-    o.d[k] = d;
+    o.rx[k] = (float)rx; o.ry[k] = (float)ry; o.rr[k] = (float)rj; o.d2o[k] = (float)d2o;
   }
 }
 
@@ -150,22 +153,23 @@ __device__ __forceinline__ void pipe_write_obs_row(const Params& p, const Agent&
       if (sidx_row) for (int k = 0; k < M; ++k) sidx_row[k] = -1;
     }
   }
+  // second loop of the sensor (:105-144): only the others' velocities still have to be fetched, as float32
+  const float prxf = (float)e.prx, pryf = (float)e.pry, raf = (float)a.rad;
+  const float vxf = (float)a.vx, vyf = (float)a.vy;
 #pragma unroll
   for (int k = 0; k < kN; ++k) {
     const int j = k + (k >= i ? 1 : 0);
     const int src = (base + j) & 31;
-    const double xj = shfl_d(a.px, src), yj = shfl_d(a.py, src), rj = shfl_d(a.rad, src);
-    const double vxj = shfl_d(a.vx, src), vyj = shfl_d(a.vy, src);
+    const float vxj = __shfl_sync(kFull, vxf, src), vyj = __shfl_sync(kFull, vyf, src);
     if (valid && key[k] != INT_MAX) {
-      const double rx = xj - a.px, ry = yj - a.py;
       float* s = row + CA_OBS_HOST_LEN + CA_OBS_OTHER_LEN * slot[k];
-      s[0] = (float)dot2(rx, ry, e.prx, e.pry);
+      s[0] = fmaf(o.ry[k], pryf, o.rx[k] * prxf);
       s[1] = (float)o.po[k];
-      s[2] = (float)dot2(vxj, vyj, e.prx, e.pry);
-      s[3] = (float)dot2(vxj, vyj, -e.pry, e.prx);
-      s[4] = (float)rj;
-      s[5] = (float)(a.rad + rj);
-      s[6] = (float)(o.d[k] - a.rad - rj);
+      s[2] = fmaf(vyj, pryf, vxj * prxf);
+      s[3] = fmaf(vyj, prxf, -(vxj * pryf));
+      s[4] = o.rr[k];
+      s[5] = raf + o.rr[k];
+      s[6] = o.d2o[k];
       if (sidx_row) sidx_row[slot[k]] = j;
     }
   }
