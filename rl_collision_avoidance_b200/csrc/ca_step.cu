@@ -210,15 +210,15 @@ const void* pipe_kernel_ptr(int A, int mb, bool dbg = false) {
 // One-shot specialised kernels: (agent slots, min CTAs/SM the register allocation targets).  The second number was
 // picked from -Xptxas -v (largest occupancy without heavy spilling) and, for A = 4, measured on B200:
 // 7 CTAs/SM lets 65 536 x 4 worlds (8192 warp chunks) finish in 2 rounds of 4144 resident warps instead of 3.
-#define CA_ONESHOT_VARIANTS(X) X(2, 8) X(3, 8) X(4, 6) X(4, 7) X(4, 8) X(5, 6) X(6, 6) X(8, 4) X(8, 5) X(10, 3) X(10, 4)
+#define CA_ONESHOT_VARIANTS(X) X(2, 8) X(3, 8) X(4, 6) X(4, 7) X(4, 8) X(4, 9) X(5, 6) X(6, 6) X(8, 4) X(8, 5) X(8, 6) X(10, 3) X(10, 4) X(10, 5)
 
 int default_oneshot_min_blocks(int A) {
   switch (A) {
     case 2: case 3: return 8;
-    case 4: return 7;
+    case 4: return 7;          // measured: 6 -> 18.0, 7 -> 17.6, 8 -> 17.8, 9 -> 19.1 us at 4 x 65536
     case 5: case 6: return 6;
-    case 8: return 5;
-    default: return 4;
+    case 8: return 6;          // measured: 5 -> 31.1 (before the register diet), 6 -> 26.3 us at 8 x 32768
+    default: return 5;         // A = 10, measured: 4 -> 25.8, 5 -> 24.1 us at 10 x 16384
   }
 }
 
