@@ -259,6 +259,48 @@ int ca_lstm_step(const float* obs, int32_t obs_stride, const float* zh, const fl
                  const float* avg7, const float* std7, float* c, float* h, int32_t batch, int32_t t, int device,
                  void* stream);
 
+/* ---- fused predictor: ThreadPredictor.run (GA3C/ThreadPredictor.py:40-75) -> NetworkVP_rnn forward
+ * (GA3C/NetworkVP_rnn.py:39-108, GA3C/NetworkVPCore.py:64-77) -> ProcessAgent.select_action (GA3C/ProcessAgent.py:98-103)
+ * as ONE kernel launch over all observation rows (tcgen05 tensor-core products, fp16 operands / fp32 accumulation).
+ *
+ * ca_predictor_params: device pointers to the float32 parameters in the TF-1.x variable layout (kernels are [in][out],
+ * row-major) — rnn/lstm_cell/{kernel [71][256], bias [256]} (rows 0..6 other-agent state, 7..70 h; gate order i, j, f, o;
+ * forget bias 1.0 is added by the library), layer1/{kernel [68][256] (rows 0..3 host state, 4..67 h), bias},
+ * layer2, fullyconnected1 ([256][256]), logits_p ([256][11]), logits_v ([256][1]) and the NN-input normalisation
+ * vectors NN_INPUT_AVG_VECTOR / NN_INPUT_STD_VECTOR (GA3C/Config.py:64-71; at least 12 entries are read). */
+typedef struct ca_predictor_params {
+  const float* lstm_kernel;
+  const float* lstm_bias;
+  const float* layer1_kernel;
+  const float* layer1_bias;
+  const float* layer2_kernel;
+  const float* layer2_bias;
+  const float* fc1_kernel;
+  const float* fc1_bias;
+  const float* logits_p_kernel;
+  const float* logits_p_bias;
+  const float* logits_v_kernel;
+  const float* logits_v_bias;
+  const float* input_avg;
+  const float* input_std;
+} ca_predictor_params;
+
+/* size of the packed parameter image ca_predictor_pack writes and ca_predict reads (device memory, 128-byte aligned) */
+#define CA_PREDICTOR_BLOB_BYTES 356512
+
+/* Re-pack the parameters into the kernel's shared-memory images (call once per weight update; stream-ordered). */
+int ca_predictor_pack(const ca_predictor_params* params, void* blob, int device, void* stream);
+
+/* One forward pass over `batch` raw observation rows (float32, row stride obs_stride floats; column 0 is_learning,
+ * 1 num_other_agents = LSTM sequence length, 2..5 host state, 6+7t..12+7t other agent t; num_others <= 22 LSTM steps).
+ * Outputs (each nullable): p [batch][11] softmax policy with MIN_POLICY mixing, v [batch], actions int32 [batch] =
+ * argmax(p) when greedy != 0 (PLAY_MODE / EVALUATE_MODE), else one draw from p per row (counter-based generator keyed by
+ * (seed, offset, row): pass a new offset every call).  error_flag (nullable, device int32) is set to 1 if an internal
+ * barrier wait times out (the kernel then traps instead of hanging). */
+int ca_predict(const float* obs, int32_t obs_stride, int32_t batch, int32_t num_others, const void* blob, float* p, float* v,
+               int32_t* actions, int32_t greedy, float min_policy, uint64_t seed, uint64_t offset, int32_t* error_flag,
+               int device, void* stream);
+
 const char* ca_strerror(int code);
 const char* ca_last_error(void);
 int ca_abi_version(void);

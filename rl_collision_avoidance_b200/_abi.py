@@ -75,6 +75,17 @@ class CaGa3cBuffers(C.Structure):
     ]
 
 
+class CaPredictorParams(C.Structure):
+    """ca_predictor_params: device pointers to the float32 parameters in the TF variable layout."""
+    FIELDS = ("lstm_kernel", "lstm_bias", "layer1_kernel", "layer1_bias", "layer2_kernel", "layer2_bias", "fc1_kernel",
+              "fc1_bias", "logits_p_kernel", "logits_p_bias", "logits_v_kernel", "logits_v_bias", "input_avg", "input_std")
+    _fields_ = [(n, C.c_void_p) for n in FIELDS]
+
+
+CA_PREDICTOR_BLOB_BYTES = 356512
+CA_PREDICTOR_MAX_OTHERS = 22
+
+
 class CaScenarioConfig(C.Structure):
     _fields_ = [("min_agents", C.c_int32), ("max_agents", C.c_int32), ("side_split_agents", C.c_int32),
                 ("ensure_learner", C.c_int32)] + \

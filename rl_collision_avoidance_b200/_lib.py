@@ -12,14 +12,15 @@ from . import _abi
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC_DIR = os.path.join(PKG_DIR, "csrc")
 LIB_PATH = os.path.join(PKG_DIR, "libcastep.so")
-SOURCES = ["ca_step.cu"]
+SOURCES = ["ca_step.cu", "ca_predict.cu"]
+OBJ_DIR = os.path.join(CSRC_DIR, "_obj")
 HEADERS = [os.path.join(CSRC_DIR, "ca_kernels.cuh"), os.path.join(CSRC_DIR, "ca_step_fast.cuh"), os.path.join(CSRC_DIR, "ca_step_pipe.cuh"), os.path.join(CSRC_DIR, "ca_ga3c.cuh"), os.path.join(CSRC_DIR, "ca_scenarios.cuh"), os.path.join(PKG_DIR, "..", "include", "ca_step.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",  # B200 only
     "-O3", "-lineinfo",
     "-fmad=false",  # float64 parity: never contract a*b+c (explicit __fma_rn where NumPy fuses)
-    "-shared", "-Xcompiler", "-fPIC", "-std=c++17",
+    "-Xcompiler", "-fPIC", "-std=c++17",
 ]
 
 # every symbol include/ca_step.h declares
@@ -27,6 +28,7 @@ EXPORTS = [
     "ca_default_config", "ca_create", "ca_destroy", "ca_set_world_state", "ca_set_reset_state", "ca_reset", "ca_step", "ca_step_host",
     "ca_reset_host", "ca_get_state", "ca_launch_count", "ca_host_alloc", "ca_host_free", "ca_nstep_returns",
     "ca_ga3c_record", "ca_ga3c_episode_stats", "ca_default_scenario_config", "ca_generate_scenarios", "ca_lstm_step",
+    "ca_predictor_pack", "ca_predict",
     "ca_strerror", "ca_last_error", "ca_abi_version",
 ]
 
@@ -45,16 +47,30 @@ def needs_build():
 
 
 def build(force=False, verbose=False):
-    """Compile csrc/*.cu for sm_100a into libcastep.so next to this file (in-tree, travels with the repo)."""
+    """Compile csrc/*.cu for sm_100a (one object per source, in parallel) and link libcastep.so next to this file
+    (in-tree, travels with the repo)."""
     if not force and not needs_build():
         return LIB_PATH
-    cmd = [nvcc_path()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
-          ["-o", LIB_PATH] + [os.path.join(CSRC_DIR, s) for s in SOURCES]
+    os.makedirs(OBJ_DIR, exist_ok=True)
+    jobs = []
+    for src in SOURCES:
+        obj = os.path.join(OBJ_DIR, src.replace(".cu", ".o"))
+        path = os.path.join(CSRC_DIR, src)
+        deps = [path] + HEADERS
+        if force or not os.path.exists(obj) or any(os.path.getmtime(d) > os.path.getmtime(obj) for d in deps):
+            cmd = [nvcc_path()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", "-o", obj, path]
+            jobs.append((cmd, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+    for cmd, proc in jobs:
+        out, _ = proc.communicate()
+        if proc.returncode != 0:
+            raise RuntimeError("nvcc failed:\n%s\n%s" % (" ".join(cmd), out))
+        if verbose:
+            print(out)
+    objs = [os.path.join(OBJ_DIR, s.replace(".cu", ".o")) for s in SOURCES]
+    cmd = [nvcc_path(), "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", LIB_PATH] + objs
     res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if res.returncode != 0:
-        raise RuntimeError("nvcc failed:\n%s\n%s" % (" ".join(cmd), res.stdout))
-    if verbose:
-        print(res.stdout)
+        raise RuntimeError("link failed:\n%s\n%s" % (" ".join(cmd), res.stdout))
     return LIB_PATH
 
 
@@ -95,6 +111,8 @@ def lib():
     L.ca_default_scenario_config.argtypes = [C.POINTER(_abi.CaScenarioConfig), i32]
     L.ca_generate_scenarios.argtypes = [vp, C.POINTER(_abi.CaScenarioConfig), C.c_uint64, C.c_int, vp]
     L.ca_lstm_step.argtypes = [vp, i32, vp, vp, vp, vp, vp, vp, vp, i32, i32, C.c_int, vp]
+    L.ca_predictor_pack.argtypes = [C.POINTER(_abi.CaPredictorParams), vp, C.c_int, vp]
+    L.ca_predict.argtypes = [vp, i32, i32, i32, vp, vp, vp, vp, i32, C.c_float, C.c_uint64, C.c_uint64, vp, C.c_int, vp]
     L.ca_strerror.argtypes = [C.c_int]
     L.ca_strerror.restype = C.c_char_p
     L.ca_last_error.restype = C.c_char_p

@@ -52,6 +52,9 @@ struct DeviceGuard {
 
 }  // namespace
 
+// used by the other translation units of the library (ca_predict.cu) to record a message for ca_last_error()
+int ca_fail_external(int code, const char* msg) { return fail(code, "%s", msg); }
+
 struct ca_env {
   ca_config cfg;
   int W = 0, A = 0, M = 0, L = 0, wpw = 0;

@@ -20,6 +20,7 @@ import re
 import torch
 
 from .Config import get_config
+from .. import _abi
 
 
 def _glorot_uniform(fan_in, fan_out, generator):
@@ -206,6 +207,63 @@ class NetworkVP_rnn(object):
         p = (torch.softmax(logits, dim=1) + net.min_policy) / (1.0 + net.min_policy * net.num_actions)
         return p, v
 
+    # ---- fused predictor (csrc/ca_predict.cu): the whole forward pass + action selection in one tcgen05 kernel launch
+    def fused_supported(self):
+        return self.device.type == "cuda" and self.net.M <= _abi.CA_PREDICTOR_MAX_OTHERS and self.net.HIDDEN == 64 \
+            and self.net.host_len == 4 and self.net.other_len == 7 and self.net.first == 1 and self.num_actions == 11 \
+            and self.net.normalize
+
+    def mark_weights_changed(self):
+        """Call after modifying the parameters outside train() / load(): the packed image is rebuilt on next use."""
+        self._packed_version = -1
+
+    def _packed_blob(self):
+        import ctypes as C
+        from .._lib import check, lib
+        version = (self.global_step, getattr(self, "_load_count", 0))
+        if getattr(self, "_packed_version", None) == version:
+            return self._blob
+        net = self.net
+        if not hasattr(self, "_blob"):
+            self._blob = torch.empty(_abi.CA_PREDICTOR_BLOB_BYTES, dtype=torch.uint8, device=self.device)
+            self._pred_error = torch.zeros(1, dtype=torch.int32, device=self.device)
+            self._pred_calls = 0
+        keep = [net.w("rnn/lstm_cell/kernel"), net.w("rnn/lstm_cell/bias"), net.w("layer1/kernel"), net.w("layer1/bias"),
+                net.w("layer2/kernel"), net.w("layer2/bias"), net.w("fullyconnected1/kernel"), net.w("fullyconnected1/bias"),
+                net.w("logits_p/kernel"), net.w("logits_p/bias"), net.w("logits_v/kernel"), net.w("logits_v/bias"),
+                net.avg, net.std]
+        keep = [t.detach().contiguous() for t in keep]
+        params = _abi.CaPredictorParams(*[C.c_void_p(t.data_ptr()) for t in keep])
+        stream = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+        check(lib().ca_predictor_pack(C.byref(params), C.c_void_p(self._blob.data_ptr()), self.device.index or 0, stream),
+              "ca_predictor_pack")
+        self._packed_version = version
+        return self._blob
+
+    @torch.no_grad()
+    def predict_fused(self, obs, want_p=True, want_actions=False, greedy=False, seed=0):
+        """ThreadPredictor + select_action for raw observation rows obs [B, L] (float32 CUDA, contiguous rows) in ONE
+        launch of the fused tcgen05 kernel: returns (p [B, 11] or None, v [B], actions int32 [B] or None).  fp16
+        operands / fp32 accumulation (tests/test_gpu_predictor.py states the tolerance against `net(obs[:, 1:])`)."""
+        import ctypes as C
+        from .._lib import check, lib
+        if not self.fused_supported():
+            raise RuntimeError("fused predictor needs CUDA and the GA3C-CADRL architecture (64 LSTM units, <= 22 others)")
+        B, L = obs.shape
+        if not obs.is_cuda or obs.dtype != torch.float32 or obs.stride(1) != 1:
+            raise ValueError("obs must be a float32 CUDA tensor with contiguous rows")
+        blob = self._packed_blob()
+        p = torch.empty((B, self.num_actions), dtype=torch.float32, device=obs.device) if want_p else None
+        v = torch.empty(B, dtype=torch.float32, device=obs.device)
+        actions = torch.empty(B, dtype=torch.int32, device=obs.device) if want_actions else None
+        ptr = lambda t: C.c_void_p(t.data_ptr()) if t is not None else None
+        stream = C.c_void_p(torch.cuda.current_stream(obs.device).cuda_stream)
+        self._pred_calls += 1
+        check(lib().ca_predict(ptr(obs), int(obs.stride(0)), B, self.net.M, ptr(blob), ptr(p), ptr(v), ptr(actions),
+                               1 if greedy else 0, float(self.net.min_policy), int(seed) & (2 ** 64 - 1), self._pred_calls,
+                               ptr(self._pred_error), obs.device.index or 0, stream), "ca_predict")
+        return p, v, actions
+
     def predict_p_and_v(self, x):
         p, v = self.predict_p_and_v_device(self._as_input(x))
         return p.cpu().numpy(), v.cpu().numpy()
@@ -290,6 +348,7 @@ class NetworkVP_rnn(object):
         print("[NetworkVPCore] Loading checkpoint file:", path)
         ck = torch.load(path, map_location=self.device)
         self.net.load_tf_variables(ck["variables"])
+        self._load_count = getattr(self, "_load_count", 0) + 1
         self.opt.load_state_dict(ck["adam"])
         self.global_step = int(ck["step"])
         return int(ck.get("episode", self._get_episode_from_filename(path)))

@@ -102,6 +102,12 @@ class GpuRollout(object):
         self.gen = torch.Generator(device=self.device)
         self.gen.manual_seed(int(seed))
         self.greedy = bool(cfg.PLAY_MODE or cfg.EVALUATE_MODE)
+        self.seed = int(seed)
+        # predictor: the fused tcgen05 kernel (forward pass + action selection in one launch) unless GA3C_PREDICTOR=composed
+        # asks for the fp32 path (ca_lstm_step kernel + cuBLAS dense layers + torch.multinomial)
+        import os
+        self.fused = os.environ.get("GA3C_PREDICTOR", "fused") != "composed" and \
+            hasattr(model, "fused_supported") and model.fused_supported()
         self.t = 0
         self.env.set_world_state(init, num_agents)
         self.env.reset(out_obs=self.rec.obs_slot(0))
@@ -112,11 +118,15 @@ class GpuRollout(object):
         """One env step for every world; returns (reward, done, game_over) device tensors of this step."""
         torch = self.torch
         obs = self.rec.obs_slot(self.t)                           # [W, A, L]; column 0 = is_learning
-        p, v = self.model.predict_from_obs(obs.reshape(self.N, self.L))   # ThreadPredictor: one batch over all slots
-        if self.greedy:
-            actions = torch.argmax(p, dim=1).to(torch.int32)      # ProcessAgent.select_action (:98-103)
+        if self.fused:   # ThreadPredictor + select_action: one launch over all slots
+            _, v, actions = self.model.predict_fused(obs.reshape(self.N, self.L), want_p=False, want_actions=True,
+                                                     greedy=self.greedy, seed=self.seed)
         else:
-            actions = torch.multinomial(p, 1, generator=self.gen).squeeze(1).to(torch.int32)
+            p, v = self.model.predict_from_obs(obs.reshape(self.N, self.L))
+            if self.greedy:
+                actions = torch.argmax(p, dim=1).to(torch.int32)      # ProcessAgent.select_action (:98-103)
+            else:
+                actions = torch.multinomial(p, 1, generator=self.gen).squeeze(1).to(torch.int32)
         _, reward, done, over = self.env.step(actions.view(self.W, self.A), out_obs=self.rec.obs_slot(self.t + 1))
         self.rec.record(self.t, actions, v.contiguous(), reward.view(-1), done.view(-1), over)
         self.last_actions, self.last_values = actions, v

@@ -1,6 +1,11 @@
 """GPU: throughput of the full GA3C actor->predictor loop (BASELINE configs[2]: 10 agents x 16384 worlds with the
-NetworkVP LSTM forward; configs[1] size as a second point).  Reports env-only, predictor-only and full rollout rates.
-Not the bench.py line (that is the env.step hot path); numbers are quoted in DESIGN.md §6."""
+NetworkVP LSTM forward fused; configs[1] size as a second point).  Reports the full rollout rate (predictor + action
+selection + env step + experience bookkeeping + scenario refresh) with the fused tcgen05 predictor and with the
+composed fp32 one (ca_lstm_step + cuBLAS + torch.multinomial), and each predictor alone (CUDA events).
+Not the bench.py line (that is the env.step hot path); numbers are quoted in DESIGN.md §6.
+    python scripts/bench_rollout.py [--json gpurun_out/rollout.json]"""
+import json
+import os
 import sys
 import time
 
@@ -14,7 +19,21 @@ from rl_collision_avoidance_b200.ga3c.rollout import GpuRollout
 from rl_collision_avoidance_b200.scenarios import random_worlds
 
 
-def run(cls, W, steps, tf32):
+def _events(fn, n=20, warm=3):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(n):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / n
+
+
+def run(cls, W, steps, predictor, tf32=False):
+    os.environ["GA3C_PREDICTOR"] = predictor
     cfg = getattr(cfgmod, cls)()
     cfgmod.set_config(cfg)
     torch.backends.cuda.matmul.allow_tf32 = tf32
@@ -37,21 +56,28 @@ def run(cls, W, steps, tf32):
             rows += ro.rec.take()[0].shape[0]
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
-    # predictor alone
-    x = ro.rec.obs_slot(0).reshape(W * A, -1)[:, 1:]
-    torch.cuda.synchronize(); t1 = time.perf_counter()
-    for _ in range(20):
-        model.predict_p_and_v_device(x)
-    torch.cuda.synchronize(); dp = (time.perf_counter() - t1) / 20
-    print("%s W=%d A=%d tf32=%s: rollout %.2f ms/step = %.1f M agent-steps/s (%.1f M learner rows/s emitted); predictor alone "
-          "%.2f ms/batch of %d rows" % (cls, W, A, tf32, 1e3 * dt / steps, W * A * steps / dt / 1e6, rows / dt / 1e6, 1e3 * dp, W * A),
-          flush=True)
+    obs = ro.rec.obs_slot(0).reshape(W * A, -1)
+    if predictor == "fused":
+        ms_pred = _events(lambda: model.predict_fused(obs, want_p=False, want_actions=True))
+    else:
+        ms_pred = _events(lambda: torch.multinomial(model.predict_from_obs(obs)[0], 1))
+    res = {"config": cls, "worlds": W, "agents": A, "predictor": predictor, "tf32_matmul": tf32,
+           "rollout_ms_per_step": 1e3 * dt / steps, "agent_steps_per_s": W * A * steps / dt,
+           "learner_rows_per_s": rows / dt, "predictor_ms": ms_pred, "predictor_rows": W * A}
+    print("%s W=%d A=%d predictor=%s%s: rollout %.3f ms/step = %.1f M agent-steps/s (%.1f M learner rows/s emitted); predictor + "
+          "action selection alone %.3f ms per batch of %d rows" %
+          (cls, W, A, predictor, " (tf32 matmul)" if tf32 else "", res["rollout_ms_per_step"], res["agent_steps_per_s"] / 1e6,
+           res["learner_rows_per_s"] / 1e6, ms_pred, W * A), flush=True)
     ro.close()
     cfgmod.set_config(None)
+    return res
 
 
 if __name__ == "__main__":
-    run("TrainPhase2", 16384, 60, False)
-    run("TrainPhase2", 16384, 60, True)
-    run("TrainPhase1", 65536, 60, False)
-    run("TrainPhase1", 65536, 60, True)
+    out = []
+    for cls, W in (("TrainPhase2", 16384), ("TrainPhase1", 65536)):
+        out.append(run(cls, W, 60, "fused"))
+        out.append(run(cls, W, 60, "composed"))
+    if "--json" in sys.argv:
+        with open(sys.argv[sys.argv.index("--json") + 1], "w") as f:
+            json.dump(out, f, indent=1)
