@@ -31,15 +31,23 @@ constexpr double kPi = 3.141592653589793;  // np.pi
 // ---- state layout in HBM: chunk-major AoSoA --------------------------------------------------------------------------
 // A "chunk" is what one warp processes: wpw = min(32 / A, 16) whole worlds = wpw * A (<= 32) agent slots, one per lane.
 // All state of a chunk lives in ONE contiguous, 128-byte aligned block of kBlkBytes = 2688 bytes:
-//     double field[kFields][32]      10 float64 fields x 32 lanes (px py heading vx vy time_remaining gx gy radius pref_speed)
+//     double field[8][32]            px py heading time_remaining gx gy radius pref_speed   (what a step reads)
 //     uint8  flags[32], policy[32]   per lane
 //     int32  num_agents[16]          per world of the chunk
+//     double vx[32], vy[32]          velocity (written by a step, read only by reset / get_state)
 // so a warp reads/writes each field as one coalesced 256-byte run at a constant offset from a single base pointer, and
 // a chunk's entire state can be fetched with a single TMA bulk copy (ca_step_pipe.cuh).  The reset snapshot uses the
 // same layout in a second buffer.
-enum StateField { F_PX = 0, F_PY, F_HD, F_VX, F_VY, F_TR, F_GX, F_GY, F_RAD, F_PS, kFields };
+// Order inside the block (offsets in doubles): the eight fields a step READS, then the byte/int tail, then the two
+// velocity fields, which a step only writes (it overwrites them before any use) — so the part of a block that a step
+// has to fetch is its first kBlkReadBytes = 2176 bytes.
+constexpr int kFields = 10;
+constexpr int O_PX = 0, O_PY = 32, O_HD = 64, O_TR = 96, O_GX = 128, O_GY = 160, O_RAD = 192, O_PS = 224;
+constexpr int O_TAIL = 256;                     // flags[32] u8, policy[32] u8, num_agents[16] i32
+constexpr int O_VX = 272, O_VY = 304;
 constexpr int kBlkDoubles = kFields * 32 + 16;  // 336 doubles
 constexpr int kBlkBytes = kBlkDoubles * 8;      // 2688 bytes
+constexpr int kBlkReadBytes = O_VX * 8;         // 2176 bytes: everything except vx, vy
 
 struct StateBlocks {
   double* base;  // [n_chunks][kBlkDoubles]
@@ -48,9 +56,9 @@ struct StateBlocks {
 __host__ __device__ __forceinline__ int worlds_per_chunk(int A) { return (32 / A) < 16 ? (32 / A) : 16; }
 
 __device__ __forceinline__ double* blk_ptr(const StateBlocks& s, long chunk) { return s.base + chunk * kBlkDoubles; }
-__device__ __forceinline__ uint8_t* blk_flags(double* blk) { return reinterpret_cast<uint8_t*>(blk + kFields * 32); }
-__device__ __forceinline__ uint8_t* blk_policy(double* blk) { return reinterpret_cast<uint8_t*>(blk + kFields * 32) + 32; }
-__device__ __forceinline__ int32_t* blk_nag(double* blk) { return reinterpret_cast<int32_t*>(blk + kFields * 32 + 8); }
+__device__ __forceinline__ uint8_t* blk_flags(double* blk) { return reinterpret_cast<uint8_t*>(blk + O_TAIL); }
+__device__ __forceinline__ uint8_t* blk_policy(double* blk) { return reinterpret_cast<uint8_t*>(blk + O_TAIL) + 32; }
+__device__ __forceinline__ int32_t* blk_nag(double* blk) { return reinterpret_cast<int32_t*>(blk + O_TAIL + 8); }
 
 // (world, agent) -> (chunk, lane) for kernels that are not organised warp-per-chunk
 __device__ __forceinline__ void slot_of(int w, int i, int A, long& chunk, int& lane, int& wl) {
@@ -215,22 +223,26 @@ struct Agent {
   int policy;
 };
 
+// kVel = false: the caller overwrites vx, vy before using them (every step kernel does: a moving agent gets its new
+// velocity, a finished one zero), so they are not fetched.
+template <bool kVel = true>
 __device__ __forceinline__ void load_agent(const double* blk, int lane, Agent& a) {
-  a.px = blk[F_PX * 32 + lane]; a.py = blk[F_PY * 32 + lane]; a.hd = blk[F_HD * 32 + lane];
-  a.vx = blk[F_VX * 32 + lane]; a.vy = blk[F_VY * 32 + lane]; a.tr = blk[F_TR * 32 + lane];
-  a.gx = blk[F_GX * 32 + lane]; a.gy = blk[F_GY * 32 + lane]; a.rad = blk[F_RAD * 32 + lane];
-  a.ps = blk[F_PS * 32 + lane];
+  a.px = blk[O_PX + lane]; a.py = blk[O_PY + lane]; a.hd = blk[O_HD + lane];
+  if (kVel) { a.vx = blk[O_VX + lane]; a.vy = blk[O_VY + lane]; } else { a.vx = 0.0; a.vy = 0.0; }
+  a.tr = blk[O_TR + lane];
+  a.gx = blk[O_GX + lane]; a.gy = blk[O_GY + lane]; a.rad = blk[O_RAD + lane];
+  a.ps = blk[O_PS + lane];
   a.flags = blk_flags(const_cast<double*>(blk))[lane];
   a.policy = blk_policy(const_cast<double*>(blk))[lane];
 }
 
 // write-back of one lane: the dynamic fields always, goal / static fields only when they changed
 __device__ __forceinline__ void store_agent(double* blk, int lane, const Agent& a, bool goal_too, bool all) {
-  blk[F_PX * 32 + lane] = a.px; blk[F_PY * 32 + lane] = a.py; blk[F_HD * 32 + lane] = a.hd;
-  blk[F_VX * 32 + lane] = a.vx; blk[F_VY * 32 + lane] = a.vy; blk[F_TR * 32 + lane] = a.tr;
+  blk[O_PX + lane] = a.px; blk[O_PY + lane] = a.py; blk[O_HD + lane] = a.hd;
+  blk[O_VX + lane] = a.vx; blk[O_VY + lane] = a.vy; blk[O_TR + lane] = a.tr;
   blk_flags(blk)[lane] = (uint8_t)a.flags;
-  if (goal_too || all) { blk[F_GX * 32 + lane] = a.gx; blk[F_GY * 32 + lane] = a.gy; }
-  if (all) { blk[F_RAD * 32 + lane] = a.rad; blk[F_PS * 32 + lane] = a.ps; blk_policy(blk)[lane] = (uint8_t)a.policy; }
+  if (goal_too || all) { blk[O_GX + lane] = a.gx; blk[O_GY + lane] = a.gy; }
+  if (all) { blk[O_RAD + lane] = a.rad; blk[O_PS + lane] = a.ps; blk_policy(blk)[lane] = (uint8_t)a.policy; }
 }
 
 __device__ __forceinline__ void zero_agent(Agent& a) {

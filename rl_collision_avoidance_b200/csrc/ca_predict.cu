@@ -43,7 +43,7 @@ constexpr int kOffWL2 = kOffWL1 + 10 * kKgB;          // [32][256][8]
 constexpr int kOffWFc1 = kOffWL2 + 32 * kKgB;         // [32][256][8]
 constexpr int kOffWOut = kOffWFc1 + 32 * kKgB;        // [32][16][8]: n 0..10 logits_p, 11 logits_v, rest 0
 constexpr int kOffF32 = kOffWOut + 32 * kKgOut;       // float section
-constexpr int kFbLstm = 0, kFbL1 = 256, kFbL2 = 512, kFbFc1 = 768, kFbOut = 1024;  // biases (forget bias +1 folded in)
+constexpr int kFbLstm = 0, kFbL1 = 256, kFbL2 = 512, kFbFc1 = 768, kFbOut = 1024;  // biases (LSTM: forget bias and the sigmoid 1/2 folded in)
 constexpr int kFAvgO = 1040, kFIstdO = 1048, kFAvgH = 1056, kFIstdH = 1060;        // input normalisation
 constexpr int kF32Count = 1064;
 constexpr int kBlobBytes = kOffF32 + kF32Count * 4;   // 356 512
@@ -154,10 +154,13 @@ __device__ __forceinline__ float tanh_fast(float x) {
   asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
-__device__ __forceinline__ float sigmoid_fast(float x) { return __fmaf_rn(0.5f, tanh_fast(0.5f * x), 0.5f); }
 
 __device__ __forceinline__ uint32_t pack_h2(float a, float b) {
   const __half2 h = __floats2half2_rn(fminf(fmaxf(a, -60000.f), 60000.f), fminf(fmaxf(b, -60000.f), 60000.f));
+  return *reinterpret_cast<const uint32_t*>(&h);
+}
+__device__ __forceinline__ uint32_t pack_h2_raw(float a, float b) {  // values known to be inside the fp16 range
+  const __half2 h = __floats2half2_rn(a, b);
   return *reinterpret_cast<const uint32_t*>(&h);
 }
 __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
@@ -188,7 +191,7 @@ __device__ __forceinline__ void dense_epilogue(uint32_t tmem_row, const float* b
       for (int e = 0; e < 4; ++e) {
         const int c = q * 8 + e * 2;
         const float2 b = *reinterpret_cast<const float2*>(bias + c0 + c);
-        w[e] = pack_h2(fmaxf(a[c] + b.x, 0.f), fmaxf(a[c + 1] + b.y, 0.f));
+        w[e] = pack_h2_raw(fminf(fmaxf(a[c] + b.x, 0.f), 60000.f), fminf(fmaxf(a[c + 1] + b.y, 0.f), 60000.f));
       }
       st_shared_v4(act_row + (uint32_t)(c0 / 8 + q) * kKgA, w[0], w[1], w[2], w[3]);
     }
@@ -311,19 +314,21 @@ __global__ void __launch_bounds__(kThreads, 2) predict_kernel(const Params p) {
 #pragma unroll
         for (int q = 0; q < 16; ++q) {
           const int u = u0 + q;
-          const float si = sigmoid_fast(gi[q] + bl[u]);
+          // sigmoid(x) = 0.5 tanh(x / 2) + 0.5: the i, f, o columns of the packed kernel and bias carry the 1/2 (and
+          // the forget bias 1.0), so every gate is one bias add + one tanh.approx
+          const float si = __fmaf_rn(0.5f, tanh_fast(gi[q] + bl[u]), 0.5f);
           const float tj = tanh_fast(gj[q] + bl[64 + u]);
-          const float sf = sigmoid_fast(gf[q] + bl[128 + u]);  // forget bias 1.0 is folded into the packed bias
-          const float so = sigmoid_fast(go[q] + bl[192 + u]);
+          const float sf = __fmaf_rn(0.5f, tanh_fast(gf[q] + bl[128 + u]), 0.5f);
+          const float so = __fmaf_rn(0.5f, tanh_fast(go[q] + bl[192 + u]), 0.5f);
           const float cn = __fmaf_rn(sf, c[u], si * tj);
           hn[q] = so * tanh_fast(cn);
           if (live) c[u] = cn;
         }
         if (live) {  // rows whose sequence ended keep c and h
-          st_shared_v4(act_row + (u0 / 8) * kKgA, pack_h2(hn[0], hn[1]), pack_h2(hn[2], hn[3]), pack_h2(hn[4], hn[5]),
-                       pack_h2(hn[6], hn[7]));
-          st_shared_v4(act_row + (u0 / 8 + 1) * kKgA, pack_h2(hn[8], hn[9]), pack_h2(hn[10], hn[11]),
-                       pack_h2(hn[12], hn[13]), pack_h2(hn[14], hn[15]));
+          st_shared_v4(act_row + (u0 / 8) * kKgA, pack_h2_raw(hn[0], hn[1]), pack_h2_raw(hn[2], hn[3]),
+                       pack_h2_raw(hn[4], hn[5]), pack_h2_raw(hn[6], hn[7]));
+          st_shared_v4(act_row + (u0 / 8 + 1) * kKgA, pack_h2_raw(hn[8], hn[9]), pack_h2_raw(hn[10], hn[11]),
+                       pack_h2_raw(hn[12], hn[13]), pack_h2_raw(hn[14], hn[15]));
         }
       }
       fence_async_smem();
@@ -489,6 +494,7 @@ __global__ void pack_kernel(const PackParams q) {
     float a = 0.f, b = 0.f;
     if (k < 64) { a = q.k_lstm[(7 + k) * kN + n]; b = q.k_l1[(4 + k) * kN + n]; }
     else if (k < 71) { a = q.k_lstm[(k - 64) * kN + n]; if (k < 68) b = q.k_l1[(k - 64) * kN + n]; }
+    if (n < 64 || n >= 128) a *= 0.5f;  // i, f, o gates: sigmoid(x) = 0.5 tanh(x / 2) + 0.5 (gate j = columns 64..127)
     wl[e] = to_h(a);
     w1[e] = to_h(b);
   }
@@ -504,7 +510,8 @@ __global__ void pack_kernel(const PackParams q) {
     wo[e] = to_h(a);
   }
   if (e < 256) {
-    f[kFbLstm + e] = q.b_lstm[e] + ((e >= 128 && e < 192) ? 1.0f : 0.f);  // forget_bias = 1.0 (TF1 LSTMCell default)
+    const float bl = q.b_lstm[e] + ((e >= 128 && e < 192) ? 1.0f : 0.f);  // forget_bias = 1.0 (TF1 LSTMCell default)
+    f[kFbLstm + e] = (e < 64 || e >= 128) ? 0.5f * bl : bl;
     f[kFbL1 + e] = q.b_l1[e];
     f[kFbL2 + e] = q.b_l2[e];
     f[kFbFc1 + e] = q.b_fc1[e];

@@ -195,11 +195,11 @@ __global__ void __launch_bounds__(128) generate_scenarios_kernel(const ScenarioP
       t0 = p.max_time_ratio * ((norm2d(px[i] - gx[i], py[i] - gy[i]) - p.thr) / sp[i]);
       if (!(t0 > p.dt)) t0 = p.dt;
     }
-    blk[F_PX * 32 + lane] = live ? px[i] : 0.0; blk[F_PY * 32 + lane] = live ? py[i] : 0.0;
-    blk[F_GX * 32 + lane] = live ? gx[i] : 0.0; blk[F_GY * 32 + lane] = live ? gy[i] : 0.0;
-    blk[F_HD * 32 + lane] = live ? (rng.u() * 2 * kPi - kPi) : 0.0;  // np.random.uniform(-pi, pi), test_cases.py:315
-    blk[F_VX * 32 + lane] = 0.0; blk[F_VY * 32 + lane] = 0.0; blk[F_TR * 32 + lane] = t0;
-    blk[F_RAD * 32 + lane] = live ? rd[i] : 0.0; blk[F_PS * 32 + lane] = live ? sp[i] : 0.0;
+    blk[O_PX + lane] = live ? px[i] : 0.0; blk[O_PY + lane] = live ? py[i] : 0.0;
+    blk[O_GX + lane] = live ? gx[i] : 0.0; blk[O_GY + lane] = live ? gy[i] : 0.0;
+    blk[O_HD + lane] = live ? (rng.u() * 2 * kPi - kPi) : 0.0;  // np.random.uniform(-pi, pi), test_cases.py:315
+    blk[O_VX + lane] = 0.0; blk[O_VY + lane] = 0.0; blk[O_TR + lane] = t0;
+    blk[O_RAD + lane] = live ? rd[i] : 0.0; blk[O_PS + lane] = live ? sp[i] : 0.0;
     blk_flags(blk)[lane] = 0; blk_policy(blk)[lane] = live ? (uint8_t)pol[i] : 0;
   }
 }

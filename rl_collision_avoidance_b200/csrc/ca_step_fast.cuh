@@ -78,7 +78,7 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks) ca_step_kernel(const __gri
   Agent a;
   int act = 0;
   if (world_ok) {
-    load_agent(blk, lane, a);
+    load_agent<false>(blk, lane, a);
     act = p.actions[g];
   }
   if (!valid) { zero_agent(a); act = 0; }
@@ -142,7 +142,7 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks) ca_step_kernel(const __gri
     // round later into L2 (TMA bulk prefetch), so the second round does not start with another DRAM burst.
     const long pc = chunk + p.prefetch_chunks;
     if (pc * wpw < p.W) {
-      asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(blk_ptr(p.s, pc)), "r"(kBlkBytes) : "memory");
+      asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(blk_ptr(p.s, pc)), "r"(kBlkReadBytes) : "memory");
       asm volatile("prefetch.global.L2 [%0];" ::"l"(p.actions + (size_t)pc * wpw * kA) : "memory");
     }
   }

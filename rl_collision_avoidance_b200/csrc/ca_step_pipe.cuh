@@ -45,7 +45,7 @@ __device__ __forceinline__ void tma_load_1d(void* dst_smem, const void* src_gmem
                : "memory");
 }
 
-constexpr int kStageBytes = kBlkBytes;                // one warp's state stage = one chunk block (2688 B)
+constexpr int kStageBytes = kBlkReadBytes;            // one warp's state stage = the part of a chunk block a step reads (2176 B)
 
 template <int kA>
 struct OthersLite {
@@ -216,8 +216,8 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks) ca_step_pipe_kernel(const 
     const bool ok = lane_used && w < p.W;
     pf_act = ok ? p.actions[(size_t)w * kA + i] : 0;
     if (lane == 0) {
-      mbar_arrive_expect_tx(bar, kBlkBytes);
-      tma_load_1d(stage, blk_ptr(p.s, c), kBlkBytes, bar);
+      mbar_arrive_expect_tx(bar, kBlkReadBytes);
+      tma_load_1d(stage, blk_ptr(p.s, c), kBlkReadBytes, bar);
     }
   };
 
@@ -242,7 +242,7 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks) ca_step_pipe_kernel(const 
     int n = world_ok ? blk_nag(stage)[wl] : 0;
     bool valid = world_ok && i < n;
     Agent a;
-    if (valid) load_agent(stage, lane, a); else zero_agent(a);
+    if (valid) load_agent<false>(stage, lane, a); else zero_agent(a);
     const int act = pf_act;
     __syncwarp();  // every lane has copied its state out of the stage: it may be refilled
     if (c + GW < n_chunks) prefetch(c + GW);
