@@ -33,11 +33,43 @@ if REPO not in sys.path:
 
 import numpy as np  # noqa: E402
 
+# name -> (agent slots per world, worlds per GPU, ragged agent counts, config.workload text, one-shot kernel occupancy)
+WORKLOADS = {
+    "phase1": (4, 65536, False,
+               "4-agent x 65536 worlds vectorised env.step, random-policy actions, auto-reset (BASELINE configs[1])", 7),
+    "phase2": (10, 16384, False,
+               "10-agent x 16384 worlds vectorised env.step only (the env half of BASELINE configs[2]), random-policy "
+               "actions, auto-reset", 5),
+    "ragged": (10, 32768, True,
+               "variable 2-10 agents per world (ragged, n_w = 2 + w mod 9, mean 6 live agents) x 32768 worlds, random-policy "
+               "actions, auto-reset (BASELINE configs[3]); agent-steps count live agents only", 5),
+}
 AGENTS = 4
 WORLDS_PER_GPU = 65536
 OTHERS = AGENTS - 1
-ALG_BYTES_PER_AGENT_STEP = 100 + 28 * OTHERS      # 184 B at M = 3
-WORKLOAD = "4-agent x 65536 worlds vectorised env.step, random-policy actions, auto-reset (BASELINE configs[1])"
+RAGGED = False
+MINBLOCKS = 7
+ALG_BYTES_PER_AGENT_STEP = 100 + 28 * OTHERS      # 100 + 28*M bytes; 184 B at M = 3, 352 B at M = 9
+WORKLOAD = WORKLOADS["phase1"][3]
+
+
+def select_workload(name):
+    """The default (phase1 = BASELINE configs[1]) is the bench line the driver records; the others are extra lines."""
+    global AGENTS, WORLDS_PER_GPU, OTHERS, RAGGED, MINBLOCKS, ALG_BYTES_PER_AGENT_STEP, WORKLOAD
+    AGENTS, WORLDS_PER_GPU, RAGGED, WORKLOAD, MINBLOCKS = WORKLOADS[name]
+    OTHERS = AGENTS - 1
+    ALG_BYTES_PER_AGENT_STEP = 100 + 28 * OTHERS
+
+
+def live_agents(worlds):
+    return int(agent_counts(worlds).sum()) if RAGGED else worlds * AGENTS
+
+
+def agent_counts(worlds):
+    """n_w = 2 + (w mod 9) for the ragged workload, else every slot is live."""
+    if RAGGED:
+        return (2 + (np.arange(worlds) % 9)).astype(np.int32)
+    return None
 FALLBACK_HBM_GBS = 6650.0                          # /opt/skills/guides/B200_PROFILING.md fallback
 
 
@@ -119,7 +151,7 @@ class ClockSampler(threading.Thread):
 def make_inputs(rank, n_sets, worlds):
     from rl_collision_avoidance_b200.scenarios import random_worlds
     rng = np.random.default_rng(20261017 + 1000 * rank)
-    return [random_worlds(worlds, AGENTS, rng) for _ in range(n_sets)], rng
+    return [random_worlds(worlds, AGENTS, rng, num_agents=agent_counts(worlds)) for _ in range(n_sets)], rng
 
 
 def cpu_baseline_run(seconds, worlds):
@@ -142,7 +174,7 @@ def cpu_baseline_run(seconds, worlds):
         if el >= seconds and n >= 3:
             break
     env.close()
-    return {"value": n * worlds * AGENTS / el, "unit": "agent-steps/s", "cores": cores, "kind": "port",
+    return {"value": n * live_agents(worlds) / el, "unit": "agent-steps/s", "cores": cores, "kind": "port",
             "sample": "oracle/ca_oracle.c (C restatement of the reference env.step), %d pthreads, %d worlds x %d agents, "
                       "%d steps in %.1f s; the reference's own Python/NumPy env runs ~3.5k agent-steps/s per core "
                       "(BASELINE.md §2) and cannot travel to the GPU box" % (cores, worlds, AGENTS, n, el)}
@@ -170,7 +202,7 @@ def run_reference_arm(args):
         env.step(acts[k % 8], nthreads=cores)
     el = time.perf_counter() - t0
     env.close()
-    value = args.steps * worlds * AGENTS / el
+    value = args.steps * live_agents(worlds) / el
     sample = ("oracle/ca_oracle.c port of the reference env.step on %d host threads; each step = all %d worlds x %d agents"
               % (cores, worlds, AGENTS))
     line = {
@@ -230,7 +262,7 @@ def run_ours(args):
     gen = torch.Generator(device="cuda")
     gen.manual_seed(1234 + rank)
     actions = [torch.randint(0, 11, (W, A), dtype=torch.int32, device="cuda", generator=gen) for _ in range(T)]
-    bytes_per_set = 2 * (W // 8) * 2688 + W * A * 4 + W * A * _abi.obs_len(OTHERS) * 4 + W * A * 9   # state blocks x2, actions, obs, outputs
+    bytes_per_set = 2 * (W // max(1, min(32 // A, 16))) * 2688 + W * A * 4 + W * A * _abi.obs_len(OTHERS) * 4 + W * A * 9   # state blocks x2, actions, obs, outputs
 
     def eager_step(k):
         envs[k % R].step(actions[k % T])
@@ -264,7 +296,7 @@ def run_ours(args):
     # graph replays launch the captured kernels without going through ca_step: count them explicitly
     gpu_launches = n_graph * G + (sum(e.handle.launch_count for e in envs) - launches0)
     dev_ms = max_over_ranks(dev_ms)
-    agent_steps = K * W * A
+    agent_steps = K * live_agents(W)
     value = world_size * agent_steps / (dev_ms * 1e-3)
 
     # ---- e2e: host buffers through ca_step_host (H2D actions, D2H obs/reward/done/game_over every step)
@@ -296,7 +328,7 @@ def run_ours(args):
     barrier()
     e2e_s = max_over_ranks(e2e_s)
     clocks = sampler.stop()
-    e2e_value = world_size * Ke * W * A / e2e_s
+    e2e_value = world_size * Ke * live_agents(W) / e2e_s
     h2d, d2h = henvs[0].h2d_bytes_per_step, henvs[0].d2h_bytes_per_step
     gpu_launches += Ke + 3
     for h in henvs:
@@ -305,7 +337,7 @@ def run_ours(args):
     if rank == 0:
         peak, peak_src = measured_peak()
         launch_ms = dev_ms / K
-        achieved = ALG_BYTES_PER_AGENT_STEP * W * A / (launch_ms * 1e-3) / 1e9
+        achieved = ALG_BYTES_PER_AGENT_STEP * live_agents(W) / (launch_ms * 1e-3) / 1e9
         line = {
             "metric": "agent-steps/sec", "value": value, "unit": "agent-steps/s", "n_gpus": world_size, "steps": K,
             "warmup": WU, "ms_per_step": dev_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -319,9 +351,9 @@ def run_ours(args):
                     "steps": Ke, "api": "ca_step_host (pinned host buffers, synchronous per step)"},
             "gpu_launches": gpu_launches,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": ncu_traffic_per_launch(), "peak_source": peak_src,
-                         "algorithmic_bytes_per_launch": ALG_BYTES_PER_AGENT_STEP * W * A,
-                         "kernel": "ca::ca_step_kernel<4, 7, false>", "launch_ms": launch_ms},
+                         "traffic": ncu_traffic_per_launch() if WORKLOAD == WORKLOADS["phase1"][3] else None, "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": ALG_BYTES_PER_AGENT_STEP * live_agents(W),
+                         "kernel": "ca::ca_step_kernel<%d, %d, false>" % (A, MINBLOCKS), "launch_ms": launch_ms},
         }
         if world_size == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline_run(args.cpu_seconds, 16384)
@@ -339,7 +371,10 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cpu-seconds", type=float, default=10.0, help="wall time of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="phase1", choices=sorted(WORKLOADS),
+                    help="phase1 = BASELINE configs[1] (the recorded bench line); phase2 / ragged = extra lines")
     args = ap.parse_args()
+    select_workload(args.workload)
     if args.impl == "reference":
         run_reference_arm(args)
     else:

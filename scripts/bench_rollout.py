@@ -75,9 +75,13 @@ def run(cls, W, steps, predictor, tf32=False):
 
 if __name__ == "__main__":
     out = []
-    for cls, W in (("TrainPhase2", 16384), ("TrainPhase1", 65536)):
-        out.append(run(cls, W, 60, "fused"))
-        out.append(run(cls, W, 60, "composed"))
+    if "--only" in sys.argv:   # e.g. --only TrainPhase2:16384:fused:40  (one configuration, for profiling)
+        cls, W, pred, steps = sys.argv[sys.argv.index("--only") + 1].split(":")
+        out.append(run(cls, int(W), int(steps), pred))
+    else:
+        for cls, W in (("TrainPhase2", 16384), ("TrainPhase1", 65536)):
+            out.append(run(cls, W, 60, "fused"))
+            out.append(run(cls, W, 60, "composed"))
     if "--json" in sys.argv:
         with open(sys.argv[sys.argv.index("--json") + 1], "w") as f:
             json.dump(out, f, indent=1)
