@@ -198,6 +198,16 @@ int ca_step(ca_env* env, const int32_t* actions, const double* cont_actions, flo
 int ca_step_host(ca_env* env, const int32_t* actions, const double* cont_actions, float* obs, float* reward,
                  uint8_t* done, uint8_t* game_over, int32_t* sorted_idx);
 
+/* The same call split in two, mirroring VecEnv.step_async / step_wait (openai/baselines vec_env.py — the interface
+ * MultiagentDummyVecEnv implements, GCA/envs/wrappers.py:104-109): _async enqueues H2D actions -> kernel -> D2H results on
+ * the handle's private stream and returns; _wait blocks until the results are in the caller's buffers.  The buffers must
+ * stay valid until _wait (page-locked buffers make the copies overlap with other handles' work).  One step may be in
+ * flight per handle; distinct handles are independent, so a caller driving several environments keeps the PCIe link
+ * busy by waiting on env k only after it has enqueued env k+1. */
+int ca_step_host_async(ca_env* env, const int32_t* actions, const double* cont_actions, float* obs, float* reward,
+                       uint8_t* done, uint8_t* game_over, int32_t* sorted_idx);
+int ca_step_host_wait(ca_env* env);
+
 /* ca_reset through HOST buffers (world_mask host uint8[W] or NULL; obs/sorted_idx host, sorted_idx may be NULL). */
 int ca_reset_host(ca_env* env, const uint8_t* world_mask, float* obs, int32_t* sorted_idx);
 
@@ -300,6 +310,24 @@ int ca_predictor_pack(const ca_predictor_params* params, void* blob, int device,
 int ca_predict(const float* obs, int32_t obs_stride, int32_t batch, int32_t num_others, const void* blob, float* p, float* v,
                int32_t* actions, int32_t greedy, float min_policy, uint64_t seed, uint64_t offset, int32_t* error_flag,
                int device, void* stream);
+
+/* Row plan for ca_predict_rows.  In the reference only LEARNING agents ever ask the predictor (ProcessAgent.run_episode,
+ * GA3C/ProcessAgent.py:128-133: rows whose is_learning observation is set), and dynamic_rnn runs num_other_agents steps
+ * per row (GA3C/NetworkVP_rnn.py:58-66).  ca_predict_plan lists the rows with is_learning != 0 sorted by descending LSTM
+ * sequence length into row_index int32[batch] (device) and writes counters int32[CA_PREDICT_PLAN_COUNTERS] (device):
+ * counters[0] = number of planned rows, counters[1 + b] = rows with sequence length b.  Rows that need no prediction get
+ * v = 0 and actions = 0 (both nullable).  Stream-ordered, no host synchronisation. */
+#define CA_PREDICT_PLAN_COUNTERS 64
+int ca_predict_plan(const float* obs, int32_t obs_stride, int32_t batch, int32_t num_others, int32_t* row_index,
+                    int32_t* counters, float* v, int32_t* actions, int device, void* stream);
+
+/* ca_predict over the planned rows only: row_index / n_rows = the plan's row_index and &counters[0] (device pointers; the
+ * row count is read on the device).  Outputs are written at the ORIGINAL row positions ([batch]-sized arrays, same
+ * meaning as ca_predict); rows outside the plan are not touched.  Tiles of 128 plan entries share one sequence length,
+ * so each tile runs exactly the LSTM steps its rows need. */
+int ca_predict_rows(const float* obs, int32_t obs_stride, int32_t batch, int32_t num_others, const void* blob,
+                    const int32_t* row_index, const int32_t* n_rows, float* p, float* v, int32_t* actions, int32_t greedy,
+                    float min_policy, uint64_t seed, uint64_t offset, int32_t* error_flag, int device, void* stream);
 
 const char* ca_strerror(int code);
 const char* ca_last_error(void);

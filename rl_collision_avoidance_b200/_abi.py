@@ -83,6 +83,7 @@ class CaPredictorParams(C.Structure):
 
 
 CA_PREDICTOR_BLOB_BYTES = 356512
+CA_PREDICT_PLAN_COUNTERS = 64
 CA_PREDICTOR_MAX_OTHERS = 22
 
 

@@ -32,6 +32,12 @@ struct Ga3cParams {
   const uint8_t* over;     // [N / A] game_over after step t
 };
 
+// ring slot of list element k of a list whose first element was recorded first_t_off steps ago (0 <= k <= first_t_off < R)
+__device__ __forceinline__ int ring_slot(int slot_now, int first_t_off, int k, int R) {
+  const int s = slot_now - first_t_off + k;
+  return s < 0 ? s + R : s;
+}
+
 __global__ void __launch_bounds__(128) ga3c_record_kernel(const __grid_constant__ Ga3cParams p) {
   const int g = blockIdx.x * blockDim.x + threadIdx.x;
   const int lane = threadIdx.x & 31;
@@ -62,8 +68,7 @@ __global__ void __launch_bounds__(128) ga3c_record_kernel(const __grid_constant_
         emit_last = dn && len == p.time_max + 1;             // leftover_term_exp (:65-66)
         n_main = (dn && len != p.time_max + 1) ? len : len - 1;
         for (int k = n_main - 1; k >= 0; --k) {              // :71-76, rewards overwritten in place
-          const int s = (int)((p.t - first_t_off + k) % R);
-          float* r = &p.b.rew_ring[(size_t)s * N + g];
+          float* r = &p.b.rew_ring[(size_t)ring_slot(slot_now, first_t_off, k, R) * N + g];
           Rv = p.gamma * Rv + *r;
           *r = Rv;
         }
@@ -91,28 +96,54 @@ __global__ void __launch_bounds__(128) ga3c_record_kernel(const __grid_constant_
   int warp_base = 0;
   if (lane == 31) warp_base = atomicAdd(p.b.out_count, warp_total);
   warp_base = __shfl_sync(0xffffffffu, warp_base, 31);
-  const int my_base = warp_base + incl - n_emit;
+  __syncwarp();  // the discounted returns written above are read back below by other lanes of the warp
 
-  // warp-cooperative row copy: for each lane with rows, all 32 lanes copy one row at a time (coalesced)
-  for (int src = 0; src < 32; ++src) {
-    const int cnt = __shfl_sync(0xffffffffu, n_emit, src);
-    if (cnt == 0) continue;
-    const int base = __shfl_sync(0xffffffffu, my_base, src);
-    const int g_src = __shfl_sync(0xffffffffu, g, src);
-    const int off = __shfl_sync(0xffffffffu, first_t_off, src);
-    const int nm = __shfl_sync(0xffffffffu, n_main, src);
-    for (int e = 0; e < cnt; ++e) {
-      const int row = base + e;
-      if (row >= p.b.capacity) break;  // overflow is reported through out_count > capacity
-      const int k = e < nm ? e : off;  // the optional extra row is the last list element
-      const int s = (int)((p.t - off + k) % R);
-      const float* x = p.b.obs_ring + ((size_t)s * N + g_src) * L + 1;  // drop the is_learning column
-      float* dst = p.b.out_x + (size_t)row * XL;
-      for (int q = lane; q < XL; q += 32) dst[q] = x[q];
-      if (lane == 0) {
-        p.b.out_r[row] = p.b.rew_ring[(size_t)s * N + g_src];
-        p.b.out_a[row] = p.b.act_ring[(size_t)s * N + g_src];
-      }
+  // Warp-cooperative row copy.  The warp's rows are numbered f = 0 .. warp_total-1 in lane order; row f belongs to the
+  // first lane whose inclusive prefix exceeds f.  kU rows are handled per round: all their loads are issued before the
+  // first store, so a warp keeps kU * ceil(XL / 32) independent 128-byte requests in flight instead of one (a
+  // synchronised flush emits 21 rows for every agent of the warp at once).
+  constexpr int kU = 4;
+  const float* __restrict__ ring = p.b.obs_ring;
+  float* __restrict__ out_x = p.b.out_x;
+  for (int f0 = 0; f0 < warp_total; f0 += kU) {
+    const float* x[kU];
+    float* dst[kU];
+    size_t ra[kU];   // index into rew_ring / act_ring
+    int row[kU];
+#pragma unroll
+    for (int u = 0; u < kU; ++u) {
+      const int f = f0 + u;
+      const int src = __popc(__ballot_sync(0xffffffffu, incl <= f)) & 31;   // owner lane (any lane when f is out of range: nothing is accessed)
+      const int s_incl = __shfl_sync(0xffffffffu, incl, src);
+      const int s_cnt = __shfl_sync(0xffffffffu, n_emit, src);
+      const int s_g = __shfl_sync(0xffffffffu, g, src);
+      const int s_off = __shfl_sync(0xffffffffu, first_t_off, src);
+      const int s_nm = __shfl_sync(0xffffffffu, n_main, src);
+      const int e = f - (s_incl - s_cnt);
+      row[u] = (f < warp_total) ? warp_base + f : p.b.capacity;  // rows past the capacity are dropped (out_count tells)
+      const int k = e < s_nm ? e : s_off;                         // the optional extra row is the last list element
+      const int sl = ring_slot(slot_now, s_off, (f < warp_total) ? k : 0, R);
+      ra[u] = (size_t)sl * N + s_g;
+      x[u] = ring + ra[u] * L + 1;                                // drop the is_learning column
+      dst[u] = out_x + (size_t)row[u] * XL;
+    }
+    for (int q0 = 0; q0 < XL; q0 += 32) {
+      const int q = q0 + lane;
+      float v[kU];
+#pragma unroll
+      for (int u = 0; u < kU; ++u) v[u] = (q < XL && row[u] < p.b.capacity) ? x[u][q] : 0.f;
+#pragma unroll
+      for (int u = 0; u < kU; ++u)
+        if (q < XL && row[u] < p.b.capacity) dst[u][q] = v[u];
+    }
+    int rr = p.b.capacity;   // lane u < kU writes r_ and a_ of row u
+    size_t ia = 0;
+#pragma unroll
+    for (int u = 0; u < kU; ++u)
+      if (lane == u) { rr = row[u]; ia = ra[u]; }
+    if (rr < p.b.capacity) {
+      p.b.out_r[rr] = p.b.rew_ring[ia];
+      p.b.out_a[rr] = p.b.act_ring[ia];
     }
   }
 }

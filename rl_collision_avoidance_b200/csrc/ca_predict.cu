@@ -69,8 +69,10 @@ struct Params {
   int greedy;            // argmax instead of sampling
   float min_policy;
   unsigned long long seed, offset;
-  int desc_swap;         // debug: swap the LBO / SBO fields of the shared-memory descriptors
   int* error;            // device int, set when a barrier wait times out
+  // optional row plan (ca_predict_plan): the kernel processes rows row_index[0 .. *n_rows) instead of 0 .. B
+  const int32_t* row_index;
+  const int32_t* n_rows;
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -115,8 +117,7 @@ __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::
 // Shared-memory matrix descriptor, K-major, no swizzle (cute::UMMA::SmemDescriptor): start >> 4 at [0,14), leading
 // byte offset >> 4 at [16,30) = distance between the two core matrices of one K = 16 step, stride byte offset >> 4 at
 // [32,46) = distance between 8-row groups, version 1 at [46,48), layout type 0 (no swizzle) at [61,64).
-__device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo, uint32_t sbo, int swap) {
-  if (swap) { const uint32_t t = lbo; lbo = sbo; sbo = t; }
+__device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo, uint32_t sbo) {
   return (uint64_t)((addr >> 4) & 0x3FFF) | ((uint64_t)((lbo >> 4) & 0x3FFF) << 16) |
          ((uint64_t)((sbo >> 4) & 0x3FFF) << 32) | (1ull << 46);
 }
@@ -209,7 +210,8 @@ __global__ void __launch_bounds__(kThreads, 2) predict_kernel(const Params p) {
   int* smax = reinterpret_cast<int*>(smem + kSmBar + 48);
   const int M = p.M;
   const int kg_host = 8 + M, kg_zero = 9 + M;
-  const long n_tiles = ((long)p.B + kRows - 1) / kRows;
+  const long n_rows = p.n_rows ? (long)*p.n_rows : (long)p.B;
+  const long n_tiles = (n_rows + kRows - 1) / kRows;
 
   // ---- one-time setup: parameters, barriers, tensor memory
   {
@@ -236,7 +238,6 @@ __global__ void __launch_bounds__(kThreads, 2) predict_kernel(const Params p) {
 
   uint32_t ph_w[2] = {0, 0}, ph_e[2] = {0, 0}, ph_acc = 0;
   constexpr uint32_t kIdesc256 = instr_desc(kRows, kN), kIdesc16 = instr_desc(kRows, kOutN);
-  const int sw = p.desc_swap;
 
   if (tid == 0 && (long)blockIdx.x < n_tiles) {  // LSTM weights of the first tile
     mbar_expect_tx(bar_w[0], 10 * kKgB);
@@ -244,9 +245,10 @@ __global__ void __launch_bounds__(kThreads, 2) predict_kernel(const Params p) {
   }
 
   for (long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-    const long row = tile * kRows + tid;
-    const bool ok = row < p.B;
-    const float* o = p.obs + (ok ? row : 0) * (long)p.stride;
+    const long pos = tile * kRows + tid;
+    const bool ok = pos < n_rows;
+    const long row = ok ? (p.row_index ? (long)p.row_index[pos] : pos) : 0;
+    const float* o = p.obs + row * (long)p.stride;
     // ---- stage the tile: sequence length, host features, the M other-agent rows (normalised, fp16), h = 0
     int seq = 0;
     {
@@ -284,11 +286,11 @@ __global__ void __launch_bounds__(kThreads, 2) predict_kernel(const Params p) {
         if (t == 0) { mbar_wait(bar_w[0], ph_w[0], p.error); ph_w[0] ^= 1; }
         tc_fence_after();
         // x_t part: one K = 16 product (k-group 8+t of A and the k-group after it, which meets zero weights)
-        umma(tmem, smem_desc(s_act + (8 + t) * kKgA, kKgA, 128, sw), smem_desc(s_w + 8 * kKgB, kKgB, 128, sw), kIdesc256, 0);
+        umma(tmem, smem_desc(s_act + (8 + t) * kKgA, kKgA, 128), smem_desc(s_w + 8 * kKgB, kKgB, 128), kIdesc256, 0);
         if (t > 0) {  // h part (h = 0 at t = 0)
 #pragma unroll
           for (int ks = 0; ks < 4; ++ks)
-            umma(tmem, smem_desc(s_act + ks * 2 * kKgA, kKgA, 128, sw), smem_desc(s_w + ks * 2 * kKgB, kKgB, 128, sw),
+            umma(tmem, smem_desc(s_act + ks * 2 * kKgA, kKgA, 128), smem_desc(s_w + ks * 2 * kKgB, kKgB, 128),
                  kIdesc256, 1);
         }
         umma_commit(bar_acc);
@@ -346,10 +348,10 @@ __global__ void __launch_bounds__(kThreads, 2) predict_kernel(const Params p) {
       }
       mbar_wait(bar_w[0], ph_w[0], p.error); ph_w[0] ^= 1;
       tc_fence_after();
-      umma(tmem, smem_desc(s_act + kg_host * kKgA, kKgA, 128, sw), smem_desc(s_w + 8 * kKgB, kKgB, 128, sw), kIdesc256, 0);
+      umma(tmem, smem_desc(s_act + kg_host * kKgA, kKgA, 128), smem_desc(s_w + 8 * kKgB, kKgB, 128), kIdesc256, 0);
 #pragma unroll
       for (int ks = 0; ks < 4; ++ks)
-        umma(tmem, smem_desc(s_act + ks * 2 * kKgA, kKgA, 128, sw), smem_desc(s_w + ks * 2 * kKgB, kKgB, 128, sw), kIdesc256, 1);
+        umma(tmem, smem_desc(s_act + ks * 2 * kKgA, kKgA, 128), smem_desc(s_w + ks * 2 * kKgB, kKgB, 128), kIdesc256, 1);
       umma_commit(bar_acc);
     }
     mbar_wait(bar_acc, ph_acc, p.error);
@@ -379,8 +381,8 @@ __global__ void __launch_bounds__(kThreads, 2) predict_kernel(const Params p) {
           tc_fence_after();
 #pragma unroll
           for (int ks = 0; ks < 2; ++ks)
-            umma(tmem, smem_desc(s_act + (ck * 4 + ks * 2) * kKgA, kKgA, 128, sw),
-                 smem_desc(s_w + b * kChunkBytes + ks * 2 * kKgB, kKgB, 128, sw), kIdesc256, (ck | ks) != 0);
+            umma(tmem, smem_desc(s_act + (ck * 4 + ks * 2) * kKgA, kKgA, 128),
+                 smem_desc(s_w + b * kChunkBytes + ks * 2 * kKgB, kKgB, 128), kIdesc256, (ck | ks) != 0);
           if (ck + 2 < 8) {
             umma_commit(bar_e[b]);
             mbar_wait(bar_e[b], ph_e[b], p.error); ph_e[b] ^= 1;
@@ -409,7 +411,7 @@ __global__ void __launch_bounds__(kThreads, 2) predict_kernel(const Params p) {
       tc_fence_after();
 #pragma unroll 4
       for (int ks = 0; ks < 16; ++ks)
-        umma(tmem, smem_desc(s_act + ks * 2 * kKgA, kKgA, 128, sw), smem_desc(s_w + ks * 2 * kKgOut, kKgOut, 128, sw), kIdesc16,
+        umma(tmem, smem_desc(s_act + ks * 2 * kKgA, kKgA, 128), smem_desc(s_w + ks * 2 * kKgOut, kKgOut, 128), kIdesc16,
              ks != 0);
       umma_commit(bar_acc);
     }
@@ -527,6 +529,66 @@ __global__ void pack_kernel(const PackParams q) {
   }
 }
 
+// ---- row plan: which rows need a prediction, grouped by LSTM sequence length ---------------------------------------------
+// Only learning agents act on a prediction (GA3C/ProcessAgent.py:128-133 asks the predictor for agents whose is_learning
+// observation is set; absent slots and non-learning agents never reach ThreadPredictor), and dynamic_rnn runs
+// num_other_agents steps per row.  The plan lists the learning rows sorted by descending sequence length, so that a tile
+// of 128 consecutive plan entries shares (almost always) one sequence length and its LSTM loop runs exactly that many
+// steps instead of the maximum.  counters: [0] = number of planned rows, [1 + b] = rows with sequence length b,
+// [32 + b] = scatter cursor of bucket b (all zeroed by the caller of plan_count_kernel).
+constexpr int kPlanBuckets = kMaxOthers + 1;
+
+__device__ __forceinline__ int plan_bucket(const float* o, int M) {  // -1: no prediction needed
+  if (o[0] == 0.f) return -1;
+  const float nf = fminf(fmaxf(o[1], 0.f), (float)M);
+  return (int)ceilf(nf);
+}
+
+__global__ void __launch_bounds__(256) plan_count_kernel(const float* __restrict__ obs, int stride, int B, int M,
+                                                          int32_t* __restrict__ counters) {
+  __shared__ int hist[kPlanBuckets];
+  if (threadIdx.x < kPlanBuckets) hist[threadIdx.x] = 0;
+  __syncthreads();
+  const long row = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (row < B) {
+    const int b = plan_bucket(obs + row * (long)stride, M);
+    if (b >= 0) atomicAdd(&hist[b], 1);
+  }
+  __syncthreads();
+  if (threadIdx.x < kPlanBuckets && hist[threadIdx.x] > 0) {
+    atomicAdd(&counters[1 + threadIdx.x], hist[threadIdx.x]);
+    atomicAdd(&counters[0], hist[threadIdx.x]);
+  }
+}
+
+__global__ void __launch_bounds__(256) plan_scatter_kernel(const float* __restrict__ obs, int stride, int B, int M,
+                                                            int32_t* __restrict__ counters, int32_t* __restrict__ row_index,
+                                                            float* __restrict__ v, int32_t* __restrict__ actions) {
+  __shared__ int start[kPlanBuckets];   // first plan position of bucket b (descending sequence length)
+  __shared__ int hist[kPlanBuckets], base[kPlanBuckets];
+  if (threadIdx.x == 0) {
+    int acc = 0;
+    for (int b = M; b >= 0; --b) { start[b] = acc; acc += counters[1 + b]; }
+  }
+  if (threadIdx.x < kPlanBuckets) hist[threadIdx.x] = 0;
+  __syncthreads();
+  const long row = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  int b = -1, local = 0;
+  if (row < B) {
+    b = plan_bucket(obs + row * (long)stride, M);
+    if (b >= 0) local = atomicAdd(&hist[b], 1);
+    else {  // rows without a prediction get defined outputs
+      if (v) v[row] = 0.f;
+      if (actions) actions[row] = 0;
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < kPlanBuckets && hist[threadIdx.x] > 0)
+    base[threadIdx.x] = atomicAdd(&counters[32 + threadIdx.x], hist[threadIdx.x]);
+  __syncthreads();
+  if (b >= 0) row_index[start[b] + base[b] + local] = (int32_t)row;
+}
+
 }  // namespace cap
 
 // ---- C-ABI ------------------------------------------------------------------------------------------------------------
@@ -552,11 +614,13 @@ int ca_predictor_pack(const ca_predictor_params* w, void* blob, int device, void
   return CA_OK;
 }
 
-int ca_predict(const float* obs, int32_t obs_stride, int32_t batch, int32_t num_others, const void* blob, float* p, float* v,
-               int32_t* actions, int32_t greedy, float min_policy, uint64_t seed, uint64_t offset, int32_t* error_flag,
-               int device, void* stream) {
+static int predict_launch(const float* obs, int32_t obs_stride, int32_t batch, int32_t num_others, const void* blob, float* p,
+                          float* v, int32_t* actions, int32_t greedy, float min_policy, uint64_t seed, uint64_t offset,
+                          int32_t* error_flag, const int32_t* row_index, const int32_t* n_rows, int device, void* stream) {
   if (!obs || !blob || batch < 1 || num_others < 1 || obs_stride < 6 + 7 * num_others)
     return ca_fail_external(CA_ERR_INVALID_ARG, "ca_predict: bad argument");
+  if ((row_index == nullptr) != (n_rows == nullptr))
+    return ca_fail_external(CA_ERR_INVALID_ARG, "ca_predict_rows: row_index and n_rows go together");
   if (num_others > cap::kMaxOthers)
     return ca_fail_external(CA_ERR_UNSUPPORTED, "ca_predict: more than 22 observed other agents");
   if (cudaSetDevice(device) != cudaSuccess) return ca_fail_external(CA_ERR_CUDA, "cudaSetDevice failed");
@@ -573,14 +637,45 @@ int ca_predict(const float* obs, int32_t obs_stride, int32_t batch, int32_t num_
   q.blob = static_cast<const unsigned char*>(blob);
   q.p = p; q.v = v; q.actions = actions; q.greedy = greedy; q.min_policy = min_policy;
   q.seed = seed; q.offset = offset; q.error = error_flag;
-  const char* ds = getenv("CA_PREDICT_DESC_SWAP");
-  q.desc_swap = (ds && ds[0] == '1') ? 1 : 0;
-  const long n_tiles = ((long)batch + cap::kRows - 1) / cap::kRows;
+  q.row_index = row_index; q.n_rows = n_rows;
+  const long n_tiles = ((long)batch + cap::kRows - 1) / cap::kRows;   // upper bound when a plan is given
   const long resident = 2l * n_sm;
   const int grid = (int)(n_tiles < resident ? n_tiles : resident);
   cap::predict_kernel<<<grid, cap::kThreads, cap::kSmTotal, (cudaStream_t)stream>>>(q);
   if (cudaPeekAtLastError() != cudaSuccess) return ca_fail_external(CA_ERR_CUDA, cudaGetErrorString(cudaGetLastError()));
   return CA_OK;
+}
+
+int ca_predict(const float* obs, int32_t obs_stride, int32_t batch, int32_t num_others, const void* blob, float* p, float* v,
+               int32_t* actions, int32_t greedy, float min_policy, uint64_t seed, uint64_t offset, int32_t* error_flag,
+               int device, void* stream) {
+  return predict_launch(obs, obs_stride, batch, num_others, blob, p, v, actions, greedy, min_policy, seed, offset, error_flag,
+                        nullptr, nullptr, device, stream);
+}
+
+int ca_predict_plan(const float* obs, int32_t obs_stride, int32_t batch, int32_t num_others, int32_t* row_index,
+                    int32_t* counters, float* v, int32_t* actions, int device, void* stream) {
+  if (!obs || !row_index || !counters || batch < 1 || num_others < 1 || obs_stride < 6 + 7 * num_others)
+    return ca_fail_external(CA_ERR_INVALID_ARG, "ca_predict_plan: bad argument");
+  if (num_others > cap::kMaxOthers)
+    return ca_fail_external(CA_ERR_UNSUPPORTED, "ca_predict_plan: more than 22 observed other agents");
+  if (cudaSetDevice(device) != cudaSuccess) return ca_fail_external(CA_ERR_CUDA, "cudaSetDevice failed");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (cudaMemsetAsync(counters, 0, CA_PREDICT_PLAN_COUNTERS * sizeof(int32_t), st) != cudaSuccess)
+    return ca_fail_external(CA_ERR_CUDA, "ca_predict_plan: memset failed");
+  const int blocks = (batch + 255) / 256;
+  cap::plan_count_kernel<<<blocks, 256, 0, st>>>(obs, obs_stride, batch, num_others, counters);
+  cap::plan_scatter_kernel<<<blocks, 256, 0, st>>>(obs, obs_stride, batch, num_others, counters, row_index, v, actions);
+  if (cudaPeekAtLastError() != cudaSuccess) return ca_fail_external(CA_ERR_CUDA, cudaGetErrorString(cudaGetLastError()));
+  return CA_OK;
+}
+
+int ca_predict_rows(const float* obs, int32_t obs_stride, int32_t batch, int32_t num_others, const void* blob,
+                    const int32_t* row_index, const int32_t* n_rows, float* p, float* v, int32_t* actions, int32_t greedy,
+                    float min_policy, uint64_t seed, uint64_t offset, int32_t* error_flag, int device, void* stream) {
+  if (!row_index || !n_rows) return ca_fail_external(CA_ERR_INVALID_ARG, "ca_predict_rows: NULL plan");
+  return predict_launch(obs, obs_stride, batch, num_others, blob, p, v, actions, greedy, min_policy, seed, offset, error_flag,
+                        row_index, n_rows, device, stream);
 }
 
 }  // extern "C"

@@ -538,8 +538,11 @@ int ca_step(ca_env* e, const int32_t* actions, const double* cont_actions, float
   return launch_world_kernel(e, true, p, (cudaStream_t)stream);
 }
 
-int ca_step_host(ca_env* e, const int32_t* actions, const double* cont_actions, float* obs, float* reward,
-                 uint8_t* done, uint8_t* game_over, int32_t* sorted_idx) {
+// VecEnv.step_async (openai/baselines vec_env.py, the interface MultiagentDummyVecEnv implements,
+// GCA/envs/wrappers.py:104-109): enqueue H2D actions -> step kernel -> D2H results on the handle's own stream and
+// return.  The host buffers must stay valid (and, to overlap, be page-locked) until ca_step_host_wait.
+int ca_step_host_async(ca_env* e, const int32_t* actions, const double* cont_actions, float* obs, float* reward,
+                       uint8_t* done, uint8_t* game_over, int32_t* sorted_idx) {
   if (!e || !actions || !obs || !reward || !done || !game_over) return fail(CA_ERR_INVALID_ARG, "NULL argument");
   if (!e->initialised) return fail(CA_ERR_NOT_INITIALISED, "ca_step_host before ca_set_world_state");
   DeviceGuard guard(e->cfg.device);
@@ -559,8 +562,24 @@ int ca_step_host(ca_env* e, const int32_t* actions, const double* cont_actions, 
   CA_CUDA(cudaMemcpyAsync(done, e->d_done, n, cudaMemcpyDeviceToHost, st));
   CA_CUDA(cudaMemcpyAsync(game_over, e->d_over, (size_t)e->W, cudaMemcpyDeviceToHost, st));
   if (sorted_idx) CA_CUDA(cudaMemcpyAsync(sorted_idx, e->d_sidx, n * e->M * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
-  CA_CUDA(cudaStreamSynchronize(st));
   return CA_OK;
+}
+
+// VecEnv.step_wait: block until the results of the last ca_step_host_async are in the caller's buffers.
+int ca_step_host_wait(ca_env* e) {
+  if (!e) return fail(CA_ERR_INVALID_ARG, "NULL argument");
+  if (!e->hstream) return CA_OK;  // nothing was ever enqueued
+  DeviceGuard guard(e->cfg.device);
+  CA_CUDA(cudaStreamSynchronize(e->hstream));
+  return CA_OK;
+}
+
+// VecEnv.step = step_async + step_wait
+int ca_step_host(ca_env* e, const int32_t* actions, const double* cont_actions, float* obs, float* reward,
+                 uint8_t* done, uint8_t* game_over, int32_t* sorted_idx) {
+  const int rc = ca_step_host_async(e, actions, cont_actions, obs, reward, done, game_over, sorted_idx);
+  if (rc != CA_OK) return rc;
+  return ca_step_host_wait(e);
 }
 
 int ca_reset_host(ca_env* e, const uint8_t* world_mask, float* obs, int32_t* sorted_idx) {
@@ -660,8 +679,7 @@ int ca_generate_scenarios(ca_env* e, const ca_scenario_config* c, uint64_t seed,
   p.only_consumed = only_consumed; p.dt = e->cfg.dt; p.thr = e->cfg.near_goal_threshold;
   p.max_time_ratio = e->cfg.max_time_ratio; p.seed = seed; p.offset = e->gen_calls * 4096ull;
   e->gen_calls += 1;
-  const int threads = 128;
-  ca::generate_scenarios_kernel<<<(e->W + threads - 1) / threads, threads, 0, (cudaStream_t)stream>>>(p);
+  ca::generate_scenarios_kernel<<<(e->W + ca::kGenWarps - 1) / ca::kGenWarps, ca::kGenWarps * 32, 0, (cudaStream_t)stream>>>(p);
   CA_CUDA(cudaPeekAtLastError());
   e->launches += 1;
   if (!e->initialised && !only_consumed) {

@@ -241,10 +241,13 @@ class NetworkVP_rnn(object):
         return self._blob
 
     @torch.no_grad()
-    def predict_fused(self, obs, want_p=True, want_actions=False, greedy=False, seed=0):
+    def predict_fused(self, obs, want_p=True, want_actions=False, greedy=False, seed=0, learning_only=False):
         """ThreadPredictor + select_action for raw observation rows obs [B, L] (float32 CUDA, contiguous rows) in ONE
         launch of the fused tcgen05 kernel: returns (p [B, 11] or None, v [B], actions int32 [B] or None).  fp16
-        operands / fp32 accumulation (tests/test_gpu_predictor.py states the tolerance against `net(obs[:, 1:])`)."""
+        operands / fp32 accumulation (tests/test_gpu_predictor.py states the tolerance against `net(obs[:, 1:])`).
+        learning_only=True predicts only the rows whose is_learning column is set — the rows the reference's actors send
+        to ThreadPredictor (ProcessAgent.py:128-133) — grouped by LSTM sequence length (ca_predict_plan + ca_predict_rows);
+        the other rows get v = 0, action 0 and p = 0."""
         import ctypes as C
         from .._lib import check, lib
         if not self.fused_supported():
@@ -253,12 +256,25 @@ class NetworkVP_rnn(object):
         if not obs.is_cuda or obs.dtype != torch.float32 or obs.stride(1) != 1:
             raise ValueError("obs must be a float32 CUDA tensor with contiguous rows")
         blob = self._packed_blob()
-        p = torch.empty((B, self.num_actions), dtype=torch.float32, device=obs.device) if want_p else None
+        alloc = torch.zeros if learning_only else torch.empty
+        p = alloc((B, self.num_actions), dtype=torch.float32, device=obs.device) if want_p else None
         v = torch.empty(B, dtype=torch.float32, device=obs.device)
         actions = torch.empty(B, dtype=torch.int32, device=obs.device) if want_actions else None
         ptr = lambda t: C.c_void_p(t.data_ptr()) if t is not None else None
         stream = C.c_void_p(torch.cuda.current_stream(obs.device).cuda_stream)
         self._pred_calls += 1
+        if learning_only:
+            if getattr(self, "_plan_rows", None) is None or self._plan_rows.numel() < B or self._plan_rows.device != obs.device:
+                self._plan_rows = torch.empty(B, dtype=torch.int32, device=obs.device)
+                self._plan_counters = torch.zeros(_abi.CA_PREDICT_PLAN_COUNTERS, dtype=torch.int32, device=obs.device)
+            dev = obs.device.index or 0
+            check(lib().ca_predict_plan(ptr(obs), int(obs.stride(0)), B, self.net.M, ptr(self._plan_rows),
+                                        ptr(self._plan_counters), ptr(v), ptr(actions), dev, stream), "ca_predict_plan")
+            check(lib().ca_predict_rows(ptr(obs), int(obs.stride(0)), B, self.net.M, ptr(blob), ptr(self._plan_rows),
+                                        ptr(self._plan_counters), ptr(p), ptr(v), ptr(actions), 1 if greedy else 0,
+                                        float(self.net.min_policy), int(seed) & (2 ** 64 - 1), self._pred_calls,
+                                        ptr(self._pred_error), dev, stream), "ca_predict_rows")
+            return p, v, actions
         check(lib().ca_predict(ptr(obs), int(obs.stride(0)), B, self.net.M, ptr(blob), ptr(p), ptr(v), ptr(actions),
                                1 if greedy else 0, float(self.net.min_policy), int(seed) & (2 ** 64 - 1), self._pred_calls,
                                ptr(self._pred_error), obs.device.index or 0, stream), "ca_predict")

@@ -108,6 +108,8 @@ class GpuRollout(object):
         import os
         self.fused = os.environ.get("GA3C_PREDICTOR", "fused") != "composed" and \
             hasattr(model, "fused_supported") and model.fused_supported()
+        # only learning agents ask the predictor (ProcessAgent.py:128-133); GA3C_PREDICT_ALL=1 predicts every slot
+        self.learning_only = os.environ.get("GA3C_PREDICT_ALL", "0") != "1"
         self.t = 0
         self.env.set_world_state(init, num_agents)
         self.env.reset(out_obs=self.rec.obs_slot(0))
@@ -120,7 +122,7 @@ class GpuRollout(object):
         obs = self.rec.obs_slot(self.t)                           # [W, A, L]; column 0 = is_learning
         if self.fused:   # ThreadPredictor + select_action: one launch over all slots
             _, v, actions = self.model.predict_fused(obs.reshape(self.N, self.L), want_p=False, want_actions=True,
-                                                     greedy=self.greedy, seed=self.seed)
+                                                     greedy=self.greedy, seed=self.seed, learning_only=self.learning_only)
         else:
             p, v = self.model.predict_from_obs(obs.reshape(self.N, self.L))
             if self.greedy:

@@ -157,15 +157,33 @@ class HostVecEnv(object):
         check(lib().ca_reset_host(self.handle._h, _vp(m), _vp(self.obs), _vp(self.sorted_idx)), "ca_reset_host")
         return self.obs
 
-    def step(self, actions, cont_actions=None):
+    def _stage_actions(self, actions, cont_actions):
         if actions is not self.actions_buf:
             self.actions_buf[...] = actions
         c = None
         if cont_actions is not None:
             self._pins["cont"].array[...] = cont_actions
             c = self._pins["cont"].array
+        return c
+
+    def step(self, actions, cont_actions=None):
+        c = self._stage_actions(actions, cont_actions)
         check(lib().ca_step_host(self.handle._h, _vp(self.actions_buf), _vp(c), _vp(self.obs), _vp(self.reward),
                                  _vp(self.done), _vp(self.game_over), _vp(self.sorted_idx)), "ca_step_host")
+        return self.obs, self.reward, self.done, self.game_over
+
+    def step_async(self, actions, cont_actions=None):
+        """VecEnv.step_async (baselines vec_env.py; MultiagentDummyVecEnv, GCA/envs/wrappers.py:104-109): enqueue the
+        step (H2D actions, kernel, D2H results) and return; the result buffers are valid after step_wait().  With
+        several HostVecEnv objects, calling step_async on the next one before step_wait on this one keeps the PCIe
+        link and the GPU busy at the same time."""
+        c = self._stage_actions(actions, cont_actions)
+        check(lib().ca_step_host_async(self.handle._h, _vp(self.actions_buf), _vp(c), _vp(self.obs), _vp(self.reward),
+                                       _vp(self.done), _vp(self.game_over), _vp(self.sorted_idx)), "ca_step_host_async")
+
+    def step_wait(self):
+        """VecEnv.step_wait: block until the step enqueued by step_async has delivered its results."""
+        check(lib().ca_step_host_wait(self.handle._h), "ca_step_host_wait")
         return self.obs, self.reward, self.done, self.game_over
 
     def get_state(self):

@@ -40,8 +40,8 @@ def one(M, B, trained):
     dp = (p - p_ref).abs().max().item()
     dv = (v - v_ref).abs().max().item()
     agree = (a.long() == p_ref.argmax(1)).float().mean().item()
-    print("M=%d B=%d trained=%d swap=%s: max|dp|=%.3e max|dv|=%.3e (|v|max %.2f) argmax agreement %.4f err=%d" %
-          (M, B, trained, os.environ.get("CA_PREDICT_DESC_SWAP", "0"), dp, dv, v_ref.abs().max().item(), agree, err), flush=True)
+    print("M=%d B=%d trained=%d: max|dp|=%.3e max|dv|=%.3e (|v|max %.2f) argmax agreement %.4f err=%d" %
+          (M, B, trained, dp, dv, v_ref.abs().max().item(), agree, err), flush=True)
     # timing
     for name, fn in (("fused", lambda: net.predict_fused(t_obs, want_p=False, want_actions=True)),
                      ("torch+lstm_step", lambda: net.predict_from_obs(t_obs)),
@@ -63,16 +63,9 @@ def main():
     if len(sys.argv) > 1 and sys.argv[1] == "one":
         one(int(sys.argv[2]), int(sys.argv[3]), int(sys.argv[4]))
         return
-    for swap in ("0", "1"):
-        for (M, B, trained) in ((3, 1000, 0),):
-            env = dict(os.environ, CA_PREDICT_DESC_SWAP=swap)
-            r = subprocess.run([sys.executable, __file__, "one", str(M), str(B), str(trained)], env=env, timeout=300,
-                               stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
-            print(r.stdout[-3000:], "rc", r.returncode, flush=True)
-    good = os.environ.get("CA_PREDICT_DESC_SWAP", "0")
-    for (M, B, trained) in ((3, 5003, 1), (3, 262144, 1), (9, 163840, 0)):
+    for (M, B, trained) in ((3, 1000, 0), (3, 5003, 1), (3, 262144, 1), (9, 163840, 0)):
         r = subprocess.run([sys.executable, __file__, "one", str(M), str(B), str(trained)], timeout=600,
-                           env=dict(os.environ, CA_PREDICT_DESC_SWAP=good), stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+                           stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
         print(r.stdout[-3000:], "rc", r.returncode, flush=True)
 
 

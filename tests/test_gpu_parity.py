@@ -413,6 +413,37 @@ def test_world_permutation_equivariance():
     a.close(); b.close()
 
 
+def test_step_async_wait_pipelined_envs_match_synchronous_steps():
+    """VecEnv.step_async/step_wait (ca_step_host_async/_wait): three envs driven round-robin with one step of look-ahead
+    (the bench's e2e pattern) produce bit-identical results to the same envs stepped synchronously."""
+    rng = np.random.default_rng(77)
+    W, A, T = 2051, 4, 25
+    sets = [_random_worlds(rng, W, A, 3.5, policies=(0, 0, 1, 2)) for _ in range(3)]
+    acts = rng.integers(0, 11, (T, 3, W, A)).astype(np.int32)
+    sync, pipe = [], []
+    for init, nag in sets:
+        for lst in (sync, pipe):
+            e = _host_env(_abi.default_config(W, A, auto_reset=1))
+            e.set_world_state(init, nag); e.reset()
+            lst.append(e)
+    want = []
+    for t in range(T):
+        for k in range(3):
+            o, r, d, g = sync[k].step(acts[t, k])
+            want.append((o.copy(), r.copy(), d.copy(), g.copy()))
+    seq = [(t, k) for t in range(T) for k in range(3)]
+    pipe[0].step_async(acts[0, 0])
+    for n, (t, k) in enumerate(seq):
+        if n + 1 < len(seq):
+            t1, k1 = seq[n + 1]
+            pipe[k1].step_async(acts[t1, k1])
+        got = pipe[k].step_wait()
+        for a, b in zip(got, want[n]):
+            np.testing.assert_array_equal(a, b)
+    for e in sync + pipe:
+        e.close()
+
+
 # ----------------------------------------------------------------------------- error behaviour
 
 def test_errors_are_loud():

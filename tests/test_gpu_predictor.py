@@ -104,6 +104,39 @@ def test_fused_predictor_on_env_observations(phase_cfg, phase):
     env.close()
 
 
+@pytest.mark.parametrize("phase", [1, 2])
+def test_learning_only_plan_predicts_exactly_the_learning_rows(phase_cfg, phase):
+    """ca_predict_plan + ca_predict_rows: the plan lists the is_learning rows sorted by descending sequence length; the
+    planned rows get bit-identical outputs to the all-rows launch (a row's result does not depend on its tile-mates), the
+    others get v = 0 / action 0 / p = 0."""
+    import torch
+    cfg = phase_cfg(phase)
+    M = cfg.MAX_NUM_OTHER_AGENTS_OBSERVED
+    net = _net(False)
+    rng = np.random.default_rng(5 + phase)
+    B = 20011
+    obs = _synthetic_obs(cfg, B, M, rng)
+    learning = rng.random(B) < 0.6
+    obs[:, 0] = learning
+    obs[~learning & (rng.random(B) < 0.5)] = 0.0            # absent slots: all-zero rows
+    t_obs = torch.from_numpy(obs).cuda()
+    p0, v0, a0 = net.predict_fused(t_obs, want_p=True, want_actions=True, seed=3)
+    net._pred_calls -= 1                                     # same (seed, offset) -> same uniform draws per row
+    p1, v1, a1 = net.predict_fused(t_obs, want_p=True, want_actions=True, seed=3, learning_only=True)
+    torch.cuda.synchronize()
+    assert int(net._pred_error.item()) == 0
+    lm = torch.from_numpy(learning).cuda()
+    assert torch.equal(p1[lm], p0[lm]) and torch.equal(v1[lm], v0[lm]) and torch.equal(a1[lm], a0[lm])
+    assert float(p1[~lm].abs().max()) == 0.0 and float(v1[~lm].abs().max()) == 0.0 and int(a1[~lm].abs().max()) == 0
+    counters = net._plan_counters.cpu().numpy()
+    rows = net._plan_rows.cpu().numpy()[:counters[0]]
+    assert counters[0] == learning.sum()
+    assert np.array_equal(np.sort(rows), np.nonzero(learning)[0])
+    seq = np.ceil(np.clip(obs[rows, 1], 0, M)).astype(int)
+    assert np.all(np.diff(seq) <= 0), "plan must be sorted by descending sequence length"
+    assert np.array_equal(np.bincount(seq, minlength=M + 1), counters[1:M + 2])
+
+
 def test_fused_predictor_repacks_after_training_step(phase_cfg):
     import torch
     cfg = phase_cfg(1)
