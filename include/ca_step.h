@@ -247,6 +247,8 @@ typedef struct ca_ga3c_buffers {
   int32_t* out_count;     /* [1] rows emitted so far (caller zeroes it); > capacity means rows were dropped */
   int32_t capacity;
   int32_t reserved;
+  int32_t* out_src;       /* [capacity] scratch: (ring slot * N + agent slot) of every emitted row */
+  int32_t* gathered;      /* [2] scratch: [0] rows whose x_/r_/a_ are already copied, [1] internal; zero both with out_count */
 } ca_ga3c_buffers;
 
 /* Append step t's experience of every learning agent and emit the training rows the reference's
@@ -268,6 +270,20 @@ int ca_ga3c_episode_stats(const float* obs_now, const float* reward, const uint8
 int ca_lstm_step(const float* obs, int32_t obs_stride, const float* zh, const float* Kx, const float* bias,
                  const float* avg7, const float* std7, float* c, float* h, int32_t batch, int32_t t, int device,
                  void* stream);
+
+/* ---- trainer: the LSTM cell of NetworkVP_rnn (tf.nn.rnn_cell.LSTMCell(64) under dynamic_rnn, GA3C/NetworkVP_rnn.py:63-66;
+ * gradients as tf.train.AdamOptimizer.minimize differentiates it, GA3C/NetworkVPCore.py:100-123) as one forward and one
+ * backward launch per time step.  Device pointers, float32.  z [B][256] = x_t Kx + h Kh + b, gate order i, j, f, o; seq_len =
+ * sequence_length of row r at seq_len[r * seq_stride] (the raw num_other_agents column); rows with t >= sequence_length
+ * keep their state.  forward writes the gate activations (sigmoid(i), tanh(j), sigmoid(f + 1), sigmoid(o)) to gates
+ * [B][256] and the new state to c, h [B][64].  backward takes the gradients w.r.t. the new state (dc, dh: nullable = 0) and
+ * writes dz [B][256], dc_prev [B][64] and dh_pass [B][64] (the gradient that reaches h_prev without going through z:
+ * dh for masked rows, 0 otherwise). */
+int ca_lstm_cell_forward(const float* z, const float* c_prev, const float* h_prev, const float* seq_len, int32_t seq_stride,
+                         int32_t t, float* gates, float* c, float* h, int32_t batch, int device, void* stream);
+int ca_lstm_cell_backward(const float* gates, const float* c_prev, const float* c_new, const float* seq_len,
+                          int32_t seq_stride, int32_t t, const float* dc, const float* dh, float* dz, float* dc_prev,
+                          float* dh_pass, int32_t batch, int device, void* stream);
 
 /* ---- fused predictor: ThreadPredictor.run (GA3C/ThreadPredictor.py:40-75) -> NetworkVP_rnn forward
  * (GA3C/NetworkVP_rnn.py:39-108, GA3C/NetworkVPCore.py:64-77) -> ProcessAgent.select_action (GA3C/ProcessAgent.py:98-103)

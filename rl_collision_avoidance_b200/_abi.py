@@ -72,6 +72,7 @@ class CaGa3cBuffers(C.Structure):
         ("obs_ring", C.c_void_p), ("act_ring", C.c_void_p), ("rew_ring", C.c_void_p), ("length", C.c_void_p),
         ("tcount", C.c_void_p), ("done_trained", C.c_void_p), ("out_x", C.c_void_p), ("out_r", C.c_void_p),
         ("out_a", C.c_void_p), ("out_count", C.c_void_p), ("capacity", C.c_int32), ("reserved", C.c_int32),
+        ("out_src", C.c_void_p), ("gathered", C.c_void_p),
     ]
 
 

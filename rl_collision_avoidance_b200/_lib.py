@@ -27,7 +27,7 @@ NVCC_FLAGS = [
 EXPORTS = [
     "ca_default_config", "ca_create", "ca_destroy", "ca_set_world_state", "ca_set_reset_state", "ca_reset", "ca_step", "ca_step_host", "ca_step_host_async", "ca_step_host_wait",
     "ca_reset_host", "ca_get_state", "ca_launch_count", "ca_host_alloc", "ca_host_free", "ca_nstep_returns",
-    "ca_ga3c_record", "ca_ga3c_episode_stats", "ca_default_scenario_config", "ca_generate_scenarios", "ca_lstm_step",
+    "ca_ga3c_record", "ca_ga3c_episode_stats", "ca_default_scenario_config", "ca_generate_scenarios", "ca_lstm_step", "ca_lstm_cell_forward", "ca_lstm_cell_backward",
     "ca_predictor_pack", "ca_predict", "ca_predict_plan", "ca_predict_rows",
     "ca_strerror", "ca_last_error", "ca_abi_version",
 ]
@@ -113,6 +113,8 @@ def lib():
     L.ca_default_scenario_config.argtypes = [C.POINTER(_abi.CaScenarioConfig), i32]
     L.ca_generate_scenarios.argtypes = [vp, C.POINTER(_abi.CaScenarioConfig), C.c_uint64, C.c_int, vp]
     L.ca_lstm_step.argtypes = [vp, i32, vp, vp, vp, vp, vp, vp, vp, i32, i32, C.c_int, vp]
+    L.ca_lstm_cell_forward.argtypes = [vp, vp, vp, vp, i32, i32, vp, vp, vp, i32, C.c_int, vp]
+    L.ca_lstm_cell_backward.argtypes = [vp, vp, vp, vp, i32, i32, vp, vp, vp, vp, vp, i32, C.c_int, vp]
     L.ca_predictor_pack.argtypes = [C.POINTER(_abi.CaPredictorParams), vp, C.c_int, vp]
     L.ca_predict.argtypes = [vp, i32, i32, i32, vp, vp, vp, vp, i32, C.c_float, C.c_uint64, C.c_uint64, vp, C.c_int, vp]
     L.ca_predict_plan.argtypes = [vp, i32, i32, i32, vp, vp, vp, vp, C.c_int, vp]

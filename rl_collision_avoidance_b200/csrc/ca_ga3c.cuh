@@ -11,7 +11,7 @@
 // (t mod R): the observation ring the env kernel writes into, an action ring and a (mutable) reward ring.
 // One thread per agent slot applies the list logic; emitted training rows (x = pre-step observation without
 // the is_learning column, discounted return, action index) are appended to compact output arrays, the slot
-// range being claimed with one atomicAdd per warp and the 26/68-float rows copied by the whole warp.
+// range being claimed with one atomicAdd per warp; a second kernel (ga3c_gather_kernel) copies the 26/68-float rows.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -96,54 +96,74 @@ __global__ void __launch_bounds__(128) ga3c_record_kernel(const __grid_constant_
   int warp_base = 0;
   if (lane == 31) warp_base = atomicAdd(p.b.out_count, warp_total);
   warp_base = __shfl_sync(0xffffffffu, warp_base, 31);
-  __syncwarp();  // the discounted returns written above are read back below by other lanes of the warp
 
-  // Warp-cooperative row copy.  The warp's rows are numbered f = 0 .. warp_total-1 in lane order; row f belongs to the
-  // first lane whose inclusive prefix exceeds f.  kU rows are handled per round: all their loads are issued before the
-  // first store, so a warp keeps kU * ceil(XL / 32) independent 128-byte requests in flight instead of one (a
-  // synchronised flush emits 21 rows for every agent of the warp at once).
-  constexpr int kU = 4;
+  // The thread lists its rows for the gather kernel: out_src[row] = (ring slot, agent slot) of the experience.  The
+  // 4 (L - 1)-byte observation rows themselves are copied by ga3c_gather_kernel, which runs over the flat row range with
+  // many independent loads in flight; doing the copy here (one warp walking its agents' rows one after the other) left
+  // the kernel latency-bound: 66 us for 77 MB in a normal step, 608 us for 1.2 GB in a synchronised flush (profiles/).
+  const int my_base = warp_base + incl - n_emit;
+  for (int e = 0; e < n_emit; ++e) {
+    const int row = my_base + e;
+    if (row >= p.b.capacity) break;                      // overflow is reported through out_count > capacity
+    const int k = e < n_main ? e : first_t_off;          // the optional extra row is the last list element
+    p.b.out_src[row] = ring_slot(slot_now, first_t_off, k, R) * p.N + g;
+  }
+}
+
+// Copies the training rows listed by ga3c_record_kernel: rows [*done_in, *out_count) of out_src -> out_x / out_r / out_a.
+// One warp per kGatherRows rows and round; all loads of a round are issued before the first store.
+constexpr int kGatherRows = 8;
+struct GatherParams {
+  ca_ga3c_buffers b;
+  int L;
+  int32_t* gathered;        // [0] rows already copied by earlier launches since the last take(), [1] block ticket
+};
+
+__global__ void __launch_bounds__(256) ga3c_gather_kernel(const __grid_constant__ GatherParams p) {
+  const int lane = threadIdx.x & 31;
+  const int XL = p.L - 1;
+  const int begin = p.gathered[0];
+  int end = *p.b.out_count;
+  if (end > p.b.capacity) end = p.b.capacity;
+  const int warps = gridDim.x * (blockDim.x >> 5);
+  const int gw = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const float* __restrict__ ring = p.b.obs_ring;
   float* __restrict__ out_x = p.b.out_x;
-  for (int f0 = 0; f0 < warp_total; f0 += kU) {
-    const float* x[kU];
-    float* dst[kU];
-    size_t ra[kU];   // index into rew_ring / act_ring
-    int row[kU];
+  for (int r0 = begin + gw * kGatherRows; r0 < end; r0 += warps * kGatherRows) {
+    const int mine = r0 + lane;
+    int src_l = 0;
+    if (lane < kGatherRows && mine < end) {
+      src_l = p.b.out_src[mine];
+      p.b.out_r[mine] = p.b.rew_ring[src_l];
+      p.b.out_a[mine] = p.b.act_ring[src_l];
+    }
+    const float* x[kGatherRows];
+    float* dst[kGatherRows];
+    bool ok[kGatherRows];
 #pragma unroll
-    for (int u = 0; u < kU; ++u) {
-      const int f = f0 + u;
-      const int src = __popc(__ballot_sync(0xffffffffu, incl <= f)) & 31;   // owner lane (any lane when f is out of range: nothing is accessed)
-      const int s_incl = __shfl_sync(0xffffffffu, incl, src);
-      const int s_cnt = __shfl_sync(0xffffffffu, n_emit, src);
-      const int s_g = __shfl_sync(0xffffffffu, g, src);
-      const int s_off = __shfl_sync(0xffffffffu, first_t_off, src);
-      const int s_nm = __shfl_sync(0xffffffffu, n_main, src);
-      const int e = f - (s_incl - s_cnt);
-      row[u] = (f < warp_total) ? warp_base + f : p.b.capacity;  // rows past the capacity are dropped (out_count tells)
-      const int k = e < s_nm ? e : s_off;                         // the optional extra row is the last list element
-      const int sl = ring_slot(slot_now, s_off, (f < warp_total) ? k : 0, R);
-      ra[u] = (size_t)sl * N + s_g;
-      x[u] = ring + ra[u] * L + 1;                                // drop the is_learning column
-      dst[u] = out_x + (size_t)row[u] * XL;
+    for (int u = 0; u < kGatherRows; ++u) {
+      const int src = __shfl_sync(0xffffffffu, src_l, u);
+      ok[u] = r0 + u < end;
+      x[u] = ring + (size_t)src * p.L + 1;              // drop the is_learning column
+      dst[u] = out_x + (size_t)(r0 + u) * XL;
     }
     for (int q0 = 0; q0 < XL; q0 += 32) {
       const int q = q0 + lane;
-      float v[kU];
+      float v[kGatherRows];
 #pragma unroll
-      for (int u = 0; u < kU; ++u) v[u] = (q < XL && row[u] < p.b.capacity) ? x[u][q] : 0.f;
+      for (int u = 0; u < kGatherRows; ++u) v[u] = (q < XL && ok[u]) ? x[u][q] : 0.f;
 #pragma unroll
-      for (int u = 0; u < kU; ++u)
-        if (q < XL && row[u] < p.b.capacity) dst[u][q] = v[u];
+      for (int u = 0; u < kGatherRows; ++u)
+        if (q < XL && ok[u]) dst[u][q] = v[u];
     }
-    int rr = p.b.capacity;   // lane u < kU writes r_ and a_ of row u
-    size_t ia = 0;
-#pragma unroll
-    for (int u = 0; u < kU; ++u)
-      if (lane == u) { rr = row[u]; ia = ra[u]; }
-    if (rr < p.b.capacity) {
-      p.b.out_r[rr] = p.b.rew_ring[ia];
-      p.b.out_a[rr] = p.b.act_ring[ia];
+  }
+  // the last block to finish publishes the new watermark (every block has read the old one by then)
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    if (atomicAdd(&p.gathered[1], 1) == (int)gridDim.x - 1) {
+      p.gathered[0] = end;
+      p.gathered[1] = 0;
     }
   }
 }
@@ -223,3 +243,70 @@ __global__ void __launch_bounds__(256) lstm_step_kernel(const float* __restrict_
 }
 
 }  // namespace ca
+
+namespace ca {
+
+// ---- trainer: the LSTM cell of NetworkVP_rnn as one forward and one backward kernel ---------------------------------------
+// GA3C/NetworkVP_rnn.py:63-66 builds tf.nn.rnn_cell.LSTMCell(64) under dynamic_rnn(sequence_length); TF differentiates it op
+// by op.  A framework re-expression does the same with ~12 elementwise kernels forward and ~25 backward per time step,
+// each streaming [B, 64..256] tensors through HBM.  Here the whole cell is one pass: thread = (row, unit).
+//   forward : z [B][256] = x_t Kx + h Kh + b (gate order i, j, f, o) -> gate activations (saved for backward), c', h';
+//             rows with t >= sequence_length keep c, h (dynamic_rnn copies the state through).
+//   backward: (dc', dh') -> dz [B][256], dc, and the part of dh that bypasses the cell for masked rows.
+// float32 with the accurate expf / tanhf (the trainer must match the framework's fp32 gradients, tests/test_gpu_ga3c.py).
+__device__ __forceinline__ float sigmoid_acc(float x) { return 1.f / (1.f + expf(-x)); }
+
+__global__ void __launch_bounds__(256) lstm_cell_fwd_kernel(const float* __restrict__ z, const float* __restrict__ c_prev,
+                                                            const float* __restrict__ h_prev,
+                                                            const float* __restrict__ seq_len, int seq_stride, int t,
+                                                            float* __restrict__ gates, float* __restrict__ c,
+                                                            float* __restrict__ h, int B) {
+  const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long row = idx >> 6;
+  const int u = (int)(idx & 63);
+  if (row >= B) return;
+  const float* zr = z + row * 256;
+  const float si = sigmoid_acc(zr[u]), tj = tanhf(zr[64 + u]), sf = sigmoid_acc(zr[128 + u] + 1.0f), so = sigmoid_acc(zr[192 + u]);
+  float* gr = gates + row * 256;
+  gr[u] = si; gr[64 + u] = tj; gr[128 + u] = sf; gr[192 + u] = so;
+  const float cp = c_prev[row * 64 + u];
+  const bool live = seq_len[row * (long)seq_stride] > (float)t;
+  const float cn = sf * cp + si * tj;
+  c[row * 64 + u] = live ? cn : cp;
+  h[row * 64 + u] = live ? so * tanhf(cn) : h_prev[row * 64 + u];
+}
+
+__global__ void __launch_bounds__(256) lstm_cell_bwd_kernel(const float* __restrict__ gates, const float* __restrict__ c_prev,
+                                                            const float* __restrict__ c_new,
+                                                            const float* __restrict__ seq_len, int seq_stride, int t,
+                                                            const float* __restrict__ dc, const float* __restrict__ dh,
+                                                            float* __restrict__ dz, float* __restrict__ dc_prev,
+                                                            float* __restrict__ dh_pass, int B) {
+  const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long row = idx >> 6;
+  const int u = (int)(idx & 63);
+  if (row >= B) return;
+  const long k = row * 64 + u;
+  const float gdc = dc ? dc[k] : 0.f, gdh = dh ? dh[k] : 0.f;
+  float* dzr = dz + row * 256;
+  const bool live = seq_len[row * (long)seq_stride] > (float)t;
+  if (!live) {
+    dzr[u] = 0.f; dzr[64 + u] = 0.f; dzr[128 + u] = 0.f; dzr[192 + u] = 0.f;
+    dc_prev[k] = gdc;
+    dh_pass[k] = gdh;
+    return;
+  }
+  const float* gr = gates + row * 256;
+  const float si = gr[u], tj = gr[64 + u], sf = gr[128 + u], so = gr[192 + u];
+  const float tc = tanhf(c_new[k]);
+  const float dco = gdc + gdh * so * (1.f - tc * tc);
+  dzr[u] = dco * tj * si * (1.f - si);
+  dzr[64 + u] = dco * si * (1.f - tj * tj);
+  dzr[128 + u] = dco * c_prev[k] * sf * (1.f - sf);
+  dzr[192 + u] = gdh * tc * so * (1.f - so);
+  dc_prev[k] = dco * sf;
+  dh_pass[k] = 0.f;
+}
+
+}  // namespace ca
+

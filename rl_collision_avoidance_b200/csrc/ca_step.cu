@@ -696,7 +696,7 @@ int ca_ga3c_record(const ca_ga3c_buffers* b, int64_t t, int32_t ring_slots, int3
                    const float* reward, const uint8_t* done, const uint8_t* game_over, int device, void* stream) {
   if (!b || !actions || !values || !reward || !done || !game_over) return fail(CA_ERR_INVALID_ARG, "NULL argument");
   if (!b->obs_ring || !b->act_ring || !b->rew_ring || !b->length || !b->tcount || !b->done_trained || !b->out_x ||
-      !b->out_r || !b->out_a || !b->out_count)
+      !b->out_r || !b->out_a || !b->out_count || !b->out_src || !b->gathered)
     return fail(CA_ERR_INVALID_ARG, "NULL buffer in ca_ga3c_buffers");
   if (t < 0 || num_slots < 1 || agents_per_world < 1 || num_slots % agents_per_world != 0 || obs_len < 2 || time_max < 1 ||
       ring_slots < time_max + 2 || b->capacity < 1)
@@ -708,6 +708,15 @@ int ca_ga3c_record(const ca_ga3c_buffers* b, int64_t t, int32_t ring_slots, int3
   p.gamma = gamma; p.actions = actions; p.values = values; p.reward = reward; p.done = done; p.over = game_over;
   const int threads = 128;
   ca::ga3c_record_kernel<<<(num_slots + threads - 1) / threads, threads, 0, (cudaStream_t)stream>>>(p);
+  CA_CUDA(cudaPeekAtLastError());
+  // copy the observation rows of the experiences emitted at this step (ring slots are recycled by the next env step)
+  ca::GatherParams gp;
+  gp.b = *b; gp.L = obs_len; gp.gathered = b->gathered;
+  const int rows_per_block = (256 / 32) * ca::kGatherRows;
+  long blocks = ((long)num_slots * 2 + rows_per_block - 1) / rows_per_block;   // ~2 rows per slot in a normal step
+  if (blocks > 4 * 148) blocks = 4 * 148;
+  if (blocks < 1) blocks = 1;
+  ca::ga3c_gather_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(gp);
   CA_CUDA(cudaPeekAtLastError());
   return CA_OK;
 }
@@ -722,6 +731,34 @@ int ca_ga3c_episode_stats(const float* obs_now, const float* reward, const uint8
   const int threads = 128;
   ca::ga3c_episode_stats_kernel<<<(num_worlds + threads - 1) / threads, threads, 0, (cudaStream_t)stream>>>(
       obs_now, reward, game_over, ep_reward, ep_steps, stats, num_worlds, agents_per_world, obs_len);
+  CA_CUDA(cudaPeekAtLastError());
+  return CA_OK;
+}
+
+int ca_lstm_cell_forward(const float* z, const float* c_prev, const float* h_prev, const float* seq_len, int32_t seq_stride,
+                         int32_t t, float* gates, float* c, float* h, int32_t batch, int device, void* stream) {
+  if (!z || !c_prev || !h_prev || !seq_len || !gates || !c || !h || batch < 1 || t < 0 || seq_stride < 1)
+    return fail(CA_ERR_INVALID_ARG, "bad argument");
+  DeviceGuard guard(device);
+  if (!guard.ok) return fail(CA_ERR_CUDA, "cudaSetDevice(%d) failed", device);
+  const long n = (long)batch * 64;
+  ca::lstm_cell_fwd_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(z, c_prev, h_prev, seq_len, seq_stride,
+                                                                                          t, gates, c, h, batch);
+  CA_CUDA(cudaPeekAtLastError());
+  return CA_OK;
+}
+
+int ca_lstm_cell_backward(const float* gates, const float* c_prev, const float* c_new, const float* seq_len,
+                          int32_t seq_stride, int32_t t, const float* dc, const float* dh, float* dz, float* dc_prev,
+                          float* dh_pass, int32_t batch, int device, void* stream) {
+  if (!gates || !c_prev || !c_new || !seq_len || !dz || !dc_prev || !dh_pass || batch < 1 || t < 0 || seq_stride < 1)
+    return fail(CA_ERR_INVALID_ARG, "bad argument");
+  DeviceGuard guard(device);
+  if (!guard.ok) return fail(CA_ERR_CUDA, "cudaSetDevice(%d) failed", device);
+  const long n = (long)batch * 64;
+  ca::lstm_cell_bwd_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(gates, c_prev, c_new, seq_len,
+                                                                                          seq_stride, t, dc, dh, dz, dc_prev,
+                                                                                          dh_pass, batch);
   CA_CUDA(cudaPeekAtLastError());
   return CA_OK;
 }

@@ -28,6 +28,46 @@ def _glorot_uniform(fan_in, fan_out, generator):
     return (torch.rand(fan_in, fan_out, generator=generator) * 2 - 1) * limit
 
 
+class _FusedLSTMCell(torch.autograd.Function):
+    """One LSTM time step (TF-1.x LSTMCell semantics under dynamic_rnn's sequence mask) through the fused CUDA cell kernels
+    (ca_lstm_cell_forward / ca_lstm_cell_backward): (z [B, 256], c [B, 64], h [B, 64], x_raw, t) -> (c', h').  x_raw's
+    column 0 is the sequence length.  The matmuls that produce z stay in the framework (cuBLAS), so autograd differentiates
+    them as usual."""
+
+    @staticmethod
+    def forward(ctx, z, c_prev, h_prev, x_raw, t):
+        import ctypes as C
+        from .._lib import check, lib
+        z, c_prev, h_prev = z.contiguous(), c_prev.contiguous(), h_prev.contiguous()
+        B = z.shape[0]
+        gates = torch.empty_like(z)
+        c, h = torch.empty_like(c_prev), torch.empty_like(h_prev)
+        ptr = lambda a: C.c_void_p(a.data_ptr())
+        stream = C.c_void_p(torch.cuda.current_stream(z.device).cuda_stream)
+        check(lib().ca_lstm_cell_forward(ptr(z), ptr(c_prev), ptr(h_prev), ptr(x_raw), int(x_raw.stride(0)), int(t), ptr(gates),
+                                         ptr(c), ptr(h), B, z.device.index or 0, stream), "ca_lstm_cell_forward")
+        ctx.save_for_backward(gates, c_prev, c, x_raw)
+        ctx.t = int(t)
+        return c, h
+
+    @staticmethod
+    def backward(ctx, dc, dh):
+        import ctypes as C
+        from .._lib import check, lib
+        gates, c_prev, c, x_raw = ctx.saved_tensors
+        B = gates.shape[0]
+        dc = None if dc is None else dc.contiguous()
+        dh = None if dh is None else dh.contiguous()
+        dz = torch.empty_like(gates)
+        dc_prev, dh_pass = torch.empty_like(c_prev), torch.empty_like(c_prev)
+        ptr = lambda a: None if a is None else C.c_void_p(a.data_ptr())
+        stream = C.c_void_p(torch.cuda.current_stream(gates.device).cuda_stream)
+        check(lib().ca_lstm_cell_backward(ptr(gates), ptr(c_prev), ptr(c), ptr(x_raw), int(x_raw.stride(0)), ctx.t, ptr(dc),
+                                          ptr(dh), ptr(dz), ptr(dc_prev), ptr(dh_pass), B, gates.device.index or 0, stream),
+              "ca_lstm_cell_backward")
+        return dz, dc_prev, dh_pass, None, None
+
+
 class PolicyValueNet(torch.nn.Module):
     """The function only (no optimiser): x [B, NN_INPUT_SIZE] float32 -> (softmax_p [B, num_actions], v [B])."""
 
@@ -78,6 +118,18 @@ class PolicyValueNet(torch.nn.Module):
         c = x.new_zeros((B, H))
         K, b = self.w("rnn/lstm_cell/kernel"), self.w("rnn/lstm_cell/bias")
         Kx, Kh = K[:self.other_len], K[self.other_len:]
+        if x.is_cuda and H == 64 and x.dtype == torch.float32 and os.environ.get("GA3C_FUSED_TRAIN_CELL", "1") != "0":
+            # CUDA: the input projections of all M steps are one batched matmul, each step is one cuBLAS addmm plus one
+            # fused cell kernel (forward) / one fused cell kernel plus the addmm gradients (backward)
+            xc = x.contiguous()
+            zx = (torch.matmul(others, Kx) + b).unbind(1)
+            for t in range(self.M):
+                z = zx[t] if t == 0 else torch.addmm(zx[t], h, Kh)
+                c, h = _FusedLSTMCell.apply(z, c, h, xc, t)
+            l1_in = torch.cat([host, h], dim=1)
+            l1 = torch.relu(l1_in @ self.w("layer1/kernel") + self.w("layer1/bias"))
+            l2 = torch.relu(l1 @ self.w("layer2/kernel") + self.w("layer2/bias"))
+            return torch.relu(l2 @ self.w("fullyconnected1/kernel") + self.w("fullyconnected1/bias"))
         for t in range(self.M):
             z = others[:, t] @ Kx + h @ Kh + b
             i, j, f, o = z.split(H, dim=1)

@@ -42,14 +42,16 @@ class ExperienceRecorder(object):
         self.out_x = torch.empty((self.capacity, self.L - 1), dtype=torch.float32, device=dev)
         self.out_r = torch.empty(self.capacity, dtype=torch.float32, device=dev)
         self.out_a = torch.empty(self.capacity, dtype=torch.int32, device=dev)
-        self.out_count = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.out_src = torch.empty(self.capacity, dtype=torch.int32, device=dev)
+        self._counters = torch.zeros(4, dtype=torch.int32, device=dev)   # [0] rows emitted, [1..2] gather watermark / ticket
+        self.out_count = self._counters[0:1]
         self.ep_reward = torch.zeros(self.W, dtype=torch.float32, device=dev)
         self.ep_steps = torch.zeros(self.W, dtype=torch.int32, device=dev)
         self.stats = torch.zeros(3, dtype=torch.float64, device=dev)
         p = lambda t: C.c_void_p(t.data_ptr())
         self._bufs = _abi.CaGa3cBuffers(p(self.obs_ring), p(self.act_ring), p(self.rew_ring), p(self.length), p(self.tcount),
                                         p(self.done_trained), p(self.out_x), p(self.out_r), p(self.out_a), p(self.out_count),
-                                        self.capacity, 0)
+                                        self.capacity, 0, p(self.out_src), C.c_void_p(self._counters.data_ptr() + 4))
 
     def obs_slot(self, t):
         return self.obs_ring[t % self.R]
@@ -76,8 +78,12 @@ class ExperienceRecorder(object):
         k = int(self.out_count.item())
         if k > self.capacity:
             raise RuntimeError("experience output overflow: %d rows emitted, capacity %d" % (k, self.capacity))
-        self.out_count.zero_()
+        self._counters.zero_()
         return self.out_x[:k], self.out_r[:k], self.out_a[:k]
+
+    def discard(self):
+        """Drop the rows emitted since the last take() without reading them."""
+        self._counters.zero_()
 
     def pop_stats(self):
         s = self.stats.cpu().numpy().copy()

@@ -47,10 +47,10 @@ def run(cls, W, steps, predictor, tf32=False, fixed_agents=False):
         sc.min_agents = sc.max_agents = A
     ro.env.generate_scenarios(sc, 5, only_consumed=False)
     for _ in range(5):
-        ro.step(); ro.env.generate_scenarios(sc, 5, only_consumed=True); ro.rec.out_count.zero_()
+        ro.step(); ro.env.generate_scenarios(sc, 5, only_consumed=True); ro.rec.discard()
     torch.cuda.synchronize()
     for _ in range(40 if fixed_agents else 0):   # let every world pick up a generated (fixed-size) scenario
-        ro.step(); ro.env.generate_scenarios(sc, 5, only_consumed=True); ro.rec.out_count.zero_()
+        ro.step(); ro.env.generate_scenarios(sc, 5, only_consumed=True); ro.rec.discard()
     o = ro.rec.obs_slot(ro.t)   # first use of these torch reductions loads their kernels: keep that out of the timing
     float((o[..., 5] > 0).sum()); float((o[..., 0] != 0).sum())
     torch.cuda.synchronize()
