@@ -27,8 +27,9 @@
 
 namespace cap {
 
-constexpr int kRows = 128;      // rows per tile = UMMA M = threads per CTA (thread r <-> TMEM lane r)
-constexpr int kThreads = 128;
+constexpr int kRows = 128;      // rows per tile = UMMA M = TMEM lanes
+constexpr int kThreads = 256;   // two threads per row: warp w reads TMEM lanes 32 (w & 3) .. +31 (the hardware's lane
+                                // window of a warp) and owns the column half (w >> 2) of every epilogue
 constexpr int kHid = 64;        // LSTM units
 constexpr int kN = 256;         // gate pre-activations (4 x 64) and dense width
 constexpr int kOutN = 16;       // policy logits (11) + value (1), padded to the smallest UMMA N
@@ -55,8 +56,9 @@ constexpr int kSmAct = 0;                    // 64 KB: dense activations [32 kg]
 constexpr int kSmW = 32 * kKgA;              // 40 KB weight stage (LSTM / layer1 image, or 2 x 16 KB chunks, or head)
 constexpr int kSmF32 = kSmW + 10 * kKgB;     // float section copy
 constexpr int kSmBar = kSmF32 + ((kF32Count * 4 + 127) / 128) * 128;
-constexpr int kSmTotal = kSmBar + 64;        // 5 mbarriers, TMEM base, max sequence length of the tile
-constexpr int kChunkBytes = 4 * kKgB;        // dense weights stream in K-chunks of 32 (two K = 16 products each)
+constexpr int kSmTotal = kSmBar + 128;       // 12 mbarriers, TMEM base, max sequence length of the tile
+constexpr int kChunkBytes = 2 * kKgB;        // dense weights stream in K-chunks of 16 (one product each), 8 KB
+constexpr int kStages = 5;                   // ... through a ring of 5 stages = the whole 40 KB weight region
 constexpr int kMaxOthers = 22;               // (8 + M + 2) k-groups must fit the activation buffer
 
 struct Params {
@@ -148,6 +150,13 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* r) {
       : "r"(taddr)
       : "memory");
 }
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float* r) {
+  uint32_t* u = reinterpret_cast<uint32_t*>(r);
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7])
+               : "r"(taddr)
+               : "memory");
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 __device__ __forceinline__ float tanh_fast(float x) {
@@ -177,10 +186,20 @@ __device__ __forceinline__ float uniform01(unsigned long long seed, unsigned lon
   return (float)(z >> 40) * (1.0f / 16777216.0f);
 }
 
+// Wait for the accumulator of the product in flight.  Only the issuing thread polls the mbarrier; the other warps sleep
+// in the CTA barrier, so the waiting tile does not take issue slots from the CTA that shares the SM (with every thread
+// polling, the try_wait loops were 16 % of all executed instructions, profiles/).
+__device__ __forceinline__ void acc_wait(uint32_t bar, uint32_t& phase, int* err, int tid) {
+  if (tid == 0) mbar_wait(bar, phase, err);
+  phase ^= 1;
+  __syncthreads();
+  tc_fence_after();
+}
+
 // bias + ReLU + fp16 repack of the thread's accumulator row -> activation buffer (the next product's A operand)
-__device__ __forceinline__ void dense_epilogue(uint32_t tmem_row, const float* bias, uint32_t act_row) {
+__device__ __forceinline__ void dense_epilogue(uint32_t tmem_row, const float* bias, uint32_t act_row, int half) {
 #pragma unroll 1
-  for (int c0 = 0; c0 < kN; c0 += 32) {
+  for (int c0 = half * (kN / 2); c0 < (half + 1) * (kN / 2); c0 += 32) {
     float a[32];
     tmem_ld16(tmem_row + c0, a);
     tmem_ld16(tmem_row + c0 + 16, a + 16);
@@ -202,12 +221,16 @@ __device__ __forceinline__ void dense_epilogue(uint32_t tmem_row, const float* b
 __global__ void __launch_bounds__(kThreads, 2) predict_kernel(const Params p) {
   extern __shared__ __align__(1024) unsigned char smem[];
   const int tid = threadIdx.x, warp = tid >> 5;
+  const int half = warp >> 2;                        // column half of the epilogues this thread owns
+  const int r = ((warp & 3) << 5) | (tid & 31);      // tile row = TMEM lane
   const uint32_t s_act = smem_u32(smem + kSmAct), s_w = smem_u32(smem + kSmW);
   float* fsec = reinterpret_cast<float*>(smem + kSmF32);
   const uint32_t bar0 = smem_u32(smem + kSmBar);
-  const uint32_t bar_w[2] = {bar0, bar0 + 8}, bar_e[2] = {bar0 + 16, bar0 + 24}, bar_acc = bar0 + 32;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + kSmBar + 40);
-  int* smax = reinterpret_cast<int*>(smem + kSmBar + 48);
+  // barriers: [0] whole-image loads (LSTM / layer1 / head weights), [1] accumulator, [2..6] ring stage filled,
+  // [7..11] ring stage drained
+  const uint32_t bar_img = bar0, bar_acc = bar0 + 8, bar_w0 = bar0 + 16, bar_e0 = bar0 + 16 + 8 * kStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + kSmBar + 104);
+  int* smax = reinterpret_cast<int*>(smem + kSmBar + 112);
   const int M = p.M;
   const int kg_host = 8 + M, kg_zero = 9 + M;
   const long n_rows = p.n_rows ? (long)*p.n_rows : (long)p.B;
@@ -219,7 +242,7 @@ __global__ void __launch_bounds__(kThreads, 2) predict_kernel(const Params p) {
     for (int q = tid; q < kF32Count; q += kThreads) fsec[q] = src[q];
   }
   if (tid == 0) {
-    for (int b = 0; b < 5; ++b) mbar_init(bar0 + 8 * b, 1);
+    for (int b = 0; b < 2 + 2 * kStages; ++b) mbar_init(bar0 + 8 * b, 1);
     *smax = 0;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -233,19 +256,19 @@ __global__ void __launch_bounds__(kThreads, 2) predict_kernel(const Params p) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
-  const uint32_t tmem_row = tmem + ((uint32_t)(warp * 32) << 16);  // this warp's 32 lanes; thread = lane
-  const uint32_t act_row = s_act + (uint32_t)tid * 16;             // this row's 16 bytes inside every k-group
+  const uint32_t tmem_row = tmem + ((uint32_t)((warp & 3) * 32) << 16);  // this warp's 32 lanes
+  const uint32_t act_row = s_act + (uint32_t)r * 16;                      // this row's 16 bytes inside every k-group
 
-  uint32_t ph_w[2] = {0, 0}, ph_e[2] = {0, 0}, ph_acc = 0;
+  uint32_t ph_img = 0, ph_acc = 0, ph_w = 0, ph_e = 0;   // ph_w / ph_e: one phase bit per ring stage
   constexpr uint32_t kIdesc256 = instr_desc(kRows, kN), kIdesc16 = instr_desc(kRows, kOutN);
 
   if (tid == 0 && (long)blockIdx.x < n_tiles) {  // LSTM weights of the first tile
-    mbar_expect_tx(bar_w[0], 10 * kKgB);
-    tma_load(s_w, p.blob + kOffWLstm, 10 * kKgB, bar_w[0]);
+    mbar_expect_tx(bar_img, 10 * kKgB);
+    tma_load(s_w, p.blob + kOffWLstm, 10 * kKgB, bar_img);
   }
 
   for (long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-    const long pos = tile * kRows + tid;
+    const long pos = tile * kRows + r;
     const bool ok = pos < n_rows;
     const long row = ok ? (p.row_index ? (long)p.row_index[pos] : pos) : 0;
     const float* o = p.obs + row * (long)p.stride;
@@ -257,13 +280,16 @@ __global__ void __launch_bounds__(kThreads, 2) predict_kernel(const Params p) {
       seq = (int)ceilf(nf);  // dynamic_rnn runs step t for rows with t < sequence_length
       const int wmax = __reduce_max_sync(0xffffffffu, seq);
       if ((tid & 31) == 0 && wmax > 0) atomicMax(smax, wmax);
-      for (int kg = 0; kg < 8; ++kg) st_shared_v4(act_row + kg * kKgA, 0u, 0u, 0u, 0u);
-      st_shared_v4(act_row + kg_zero * kKgA, 0u, 0u, 0u, 0u);
-      float hf[4];
+      // the two threads of a row share the staging: h = 0 for their own unit half, other agents t = half, half + 2, ...
+      for (int kg = half * 4; kg < half * 4 + 4; ++kg) st_shared_v4(act_row + kg * kKgA, 0u, 0u, 0u, 0u);
+      if (half == 0) {
+        st_shared_v4(act_row + kg_zero * kKgA, 0u, 0u, 0u, 0u);
+        float hf[4];
 #pragma unroll
-      for (int k = 0; k < 4; ++k) hf[k] = ok ? (o[2 + k] - fsec[kFAvgH + k]) * fsec[kFIstdH + k] : 0.f;
-      st_shared_v4(act_row + kg_host * kKgA, pack_h2(hf[0], hf[1]), pack_h2(hf[2], hf[3]), 0u, 0u);
-      for (int t = 0; t < M; ++t) {
+        for (int k = 0; k < 4; ++k) hf[k] = ok ? (o[2 + k] - fsec[kFAvgH + k]) * fsec[kFIstdH + k] : 0.f;
+        st_shared_v4(act_row + kg_host * kKgA, pack_h2(hf[0], hf[1]), pack_h2(hf[2], hf[3]), 0u, 0u);
+      }
+      for (int t = half; t < M; t += 2) {
         float x[8];
 #pragma unroll
         for (int k = 0; k < 7; ++k) x[k] = ok ? (o[6 + 7 * t + k] - fsec[kFAvgO + k]) * fsec[kFIstdO + k] : 0.f;
@@ -272,9 +298,9 @@ __global__ void __launch_bounds__(kThreads, 2) predict_kernel(const Params p) {
                      pack_h2(x[6], x[7]));
       }
     }
-    float c[kHid];
+    float c[kHid / 2];   // cell state of this thread's 32 units
 #pragma unroll
-    for (int u = 0; u < kHid; ++u) c[u] = 0.f;
+    for (int u = 0; u < kHid / 2; ++u) c[u] = 0.f;
     fence_async_smem();
     tc_fence_before();
     __syncthreads();
@@ -283,7 +309,7 @@ __global__ void __launch_bounds__(kThreads, 2) predict_kernel(const Params p) {
     // ---- LSTM over the other agents (GA3C/NetworkVP_rnn.py:58-66)
     for (int t = 0; t < steps; ++t) {
       if (tid == 0) {
-        if (t == 0) { mbar_wait(bar_w[0], ph_w[0], p.error); ph_w[0] ^= 1; }
+        if (t == 0) { mbar_wait(bar_img, ph_img, p.error); ph_img ^= 1; }
         tc_fence_after();
         // x_t part: one K = 16 product (k-group 8+t of A and the k-group after it, which meets zero weights)
         umma(tmem, smem_desc(s_act + (8 + t) * kKgA, kKgA, 128), smem_desc(s_w + 8 * kKgB, kKgB, 128), kIdesc256, 0);
@@ -295,26 +321,25 @@ __global__ void __launch_bounds__(kThreads, 2) predict_kernel(const Params p) {
         }
         umma_commit(bar_acc);
       }
-      mbar_wait(bar_acc, ph_acc, p.error);
-      ph_acc ^= 1;
-      tc_fence_after();
+      acc_wait(bar_acc, ph_acc, p.error, tid);
       if (tid == 0 && t == steps - 1) {  // the LSTM image is no longer needed: fetch layer1's behind the gate math
-        mbar_expect_tx(bar_w[0], 10 * kKgB);
-        tma_load(s_w, p.blob + kOffWL1, 10 * kKgB, bar_w[0]);
+        mbar_expect_tx(bar_img, 10 * kKgB);
+        tma_load(s_w, p.blob + kOffWL1, 10 * kKgB, bar_img);
       }
       const bool live = t < seq;
       const float* bl = fsec + kFbLstm;
 #pragma unroll
-      for (int u0 = 0; u0 < kHid; u0 += 16) {
-        float gi[16], gj[16], gf[16], go[16];
-        tmem_ld16(tmem_row + u0, gi);
-        tmem_ld16(tmem_row + 64 + u0, gj);
-        tmem_ld16(tmem_row + 128 + u0, gf);
-        tmem_ld16(tmem_row + 192 + u0, go);
+      for (int q0 = 0; q0 < kHid / 2; q0 += 8) {
+        const int u0 = half * (kHid / 2) + q0;   // first of 8 units = one k-group of h
+        float gi[8], gj[8], gf[8], go[8];
+        tmem_ld8(tmem_row + u0, gi);
+        tmem_ld8(tmem_row + 64 + u0, gj);
+        tmem_ld8(tmem_row + 128 + u0, gf);
+        tmem_ld8(tmem_row + 192 + u0, go);
         tmem_ld_wait();
-        float hn[16];
+        float hn[8];
 #pragma unroll
-        for (int q = 0; q < 16; ++q) {
+        for (int q = 0; q < 8; ++q) {
           const int u = u0 + q;
           // sigmoid(x) = 0.5 tanh(x / 2) + 0.5: the i, f, o columns of the packed kernel and bias carry the 1/2 (and
           // the forget bias 1.0), so every gate is one bias add + one tanh.approx
@@ -322,16 +347,13 @@ __global__ void __launch_bounds__(kThreads, 2) predict_kernel(const Params p) {
           const float tj = tanh_fast(gj[q] + bl[64 + u]);
           const float sf = __fmaf_rn(0.5f, tanh_fast(gf[q] + bl[128 + u]), 0.5f);
           const float so = __fmaf_rn(0.5f, tanh_fast(go[q] + bl[192 + u]), 0.5f);
-          const float cn = __fmaf_rn(sf, c[u], si * tj);
+          const float cn = __fmaf_rn(sf, c[q0 + q], si * tj);
           hn[q] = so * tanh_fast(cn);
-          if (live) c[u] = cn;
+          if (live) c[q0 + q] = cn;
         }
-        if (live) {  // rows whose sequence ended keep c and h
+        if (live)  // rows whose sequence ended keep c and h
           st_shared_v4(act_row + (u0 / 8) * kKgA, pack_h2_raw(hn[0], hn[1]), pack_h2_raw(hn[2], hn[3]),
                        pack_h2_raw(hn[4], hn[5]), pack_h2_raw(hn[6], hn[7]));
-          st_shared_v4(act_row + (u0 / 8 + 1) * kKgA, pack_h2_raw(hn[8], hn[9]), pack_h2_raw(hn[10], hn[11]),
-                       pack_h2_raw(hn[12], hn[13]), pack_h2_raw(hn[14], hn[15]));
-        }
       }
       fence_async_smem();
       tc_fence_before();
@@ -342,11 +364,11 @@ __global__ void __launch_bounds__(kThreads, 2) predict_kernel(const Params p) {
     if (tid == 0) {
       *smax = 0;
       if (steps == 0) {  // no row had another agent: the stage still holds (or is receiving) the LSTM image
-        mbar_wait(bar_w[0], ph_w[0], p.error); ph_w[0] ^= 1;
-        mbar_expect_tx(bar_w[0], 10 * kKgB);
-        tma_load(s_w, p.blob + kOffWL1, 10 * kKgB, bar_w[0]);
+        mbar_wait(bar_img, ph_img, p.error); ph_img ^= 1;
+        mbar_expect_tx(bar_img, 10 * kKgB);
+        tma_load(s_w, p.blob + kOffWL1, 10 * kKgB, bar_img);
       }
-      mbar_wait(bar_w[0], ph_w[0], p.error); ph_w[0] ^= 1;
+      mbar_wait(bar_img, ph_img, p.error); ph_img ^= 1;
       tc_fence_after();
       umma(tmem, smem_desc(s_act + kg_host * kKgA, kKgA, 128), smem_desc(s_w + 8 * kKgB, kKgB, 128), kIdesc256, 0);
 #pragma unroll
@@ -354,60 +376,62 @@ __global__ void __launch_bounds__(kThreads, 2) predict_kernel(const Params p) {
         umma(tmem, smem_desc(s_act + ks * 2 * kKgA, kKgA, 128), smem_desc(s_w + ks * 2 * kKgB, kKgB, 128), kIdesc256, 1);
       umma_commit(bar_acc);
     }
-    mbar_wait(bar_acc, ph_acc, p.error);
-    ph_acc ^= 1;
-    tc_fence_after();
+    acc_wait(bar_acc, ph_acc, p.error, tid);
 
-    // ---- layer2 and fullyconnected1: weights stream through two 16 KB stages, K = 32 per chunk
+    // ---- layer2 and fullyconnected1: the 128 KB of weights of a layer stream through a ring of five 8 KB stages (one
+    // K = 16 product per chunk).  A stage is refilled one chunk behind the product that reads it, so the issuing thread
+    // never waits for the product it has just issued and four copies are in flight while one chunk is consumed.
 #pragma unroll 1
     for (int layer = 0; layer < 2; ++layer) {
       const unsigned char* wsrc = p.blob + (layer == 0 ? kOffWL2 : kOffWFc1);
       if (tid == 0) {  // the previous product is complete: its weights may be overwritten while its epilogue runs
-        for (int b = 0; b < 2; ++b) {
-          mbar_expect_tx(bar_w[b], kChunkBytes);
-          tma_load(s_w + b * kChunkBytes, wsrc + b * kChunkBytes, kChunkBytes, bar_w[b]);
+        for (int st = 0; st < kStages; ++st) {
+          mbar_expect_tx(bar_w0 + 8 * st, kChunkBytes);
+          tma_load(s_w + st * kChunkBytes, wsrc + st * kChunkBytes, kChunkBytes, bar_w0 + 8 * st);
         }
       }
-      dense_epilogue(tmem_row, fsec + (layer == 0 ? kFbL1 : kFbL2), act_row);
+      dense_epilogue(tmem_row, fsec + (layer == 0 ? kFbL1 : kFbL2), act_row, half);
       fence_async_smem();
       tc_fence_before();
       __syncthreads();
       if (tid == 0) {
         tc_fence_after();
+        int st = 0, st_prev = kStages - 1;
 #pragma unroll 1
-        for (int ck = 0; ck < 8; ++ck) {
-          const int b = ck & 1;
-          mbar_wait(bar_w[b], ph_w[b], p.error); ph_w[b] ^= 1;
+        for (int ck = 0; ck < 16; ++ck) {
+          mbar_wait(bar_w0 + 8 * st, (ph_w >> st) & 1u, p.error); ph_w ^= 1u << st;
           tc_fence_after();
-#pragma unroll
-          for (int ks = 0; ks < 2; ++ks)
-            umma(tmem, smem_desc(s_act + (ck * 4 + ks * 2) * kKgA, kKgA, 128),
-                 smem_desc(s_w + b * kChunkBytes + ks * 2 * kKgB, kKgB, 128), kIdesc256, (ck | ks) != 0);
-          if (ck + 2 < 8) {
-            umma_commit(bar_e[b]);
-            mbar_wait(bar_e[b], ph_e[b], p.error); ph_e[b] ^= 1;
-            mbar_expect_tx(bar_w[b], kChunkBytes);
-            tma_load(s_w + b * kChunkBytes, wsrc + (ck + 2) * kChunkBytes, kChunkBytes, bar_w[b]);
+          umma(tmem, smem_desc(s_act + ck * 2 * kKgA, kKgA, 128), smem_desc(s_w + st * kChunkBytes, kKgB, 128), kIdesc256,
+               ck != 0);
+          umma_commit(bar_e0 + 8 * st);
+          if (ck >= 1) {   // the stage of chunk ck - 1: wait for its product (the drained barrier is consumed every time,
+                           // so its phase stays in step) and refill it with chunk ck - 1 + kStages if there is one
+            mbar_wait(bar_e0 + 8 * st_prev, (ph_e >> st_prev) & 1u, p.error); ph_e ^= 1u << st_prev;
+            if (ck - 1 + kStages < 16) {
+              mbar_expect_tx(bar_w0 + 8 * st_prev, kChunkBytes);
+              tma_load(s_w + st_prev * kChunkBytes, wsrc + (ck - 1 + kStages) * kChunkBytes, kChunkBytes, bar_w0 + 8 * st_prev);
+            }
           }
+          st_prev = st;
+          st = st + 1 == kStages ? 0 : st + 1;
         }
+        mbar_wait(bar_e0 + 8 * st_prev, (ph_e >> st_prev) & 1u, p.error); ph_e ^= 1u << st_prev;   // chunk 15: all products done
         umma_commit(bar_acc);
       }
-      mbar_wait(bar_acc, ph_acc, p.error);
-      ph_acc ^= 1;
-      tc_fence_after();
+      acc_wait(bar_acc, ph_acc, p.error, tid);
     }
 
     // ---- heads: logits_p (11) and logits_v (1) as one N = 16 product
     if (tid == 0) {
-      mbar_expect_tx(bar_w[0], 32 * kKgOut);
-      tma_load(s_w, p.blob + kOffWOut, 32 * kKgOut, bar_w[0]);
+      mbar_expect_tx(bar_img, 32 * kKgOut);
+      tma_load(s_w, p.blob + kOffWOut, 32 * kKgOut, bar_img);
     }
-    dense_epilogue(tmem_row, fsec + kFbFc1, act_row);
+    dense_epilogue(tmem_row, fsec + kFbFc1, act_row, half);
     fence_async_smem();
     tc_fence_before();
     __syncthreads();
     if (tid == 0) {
-      mbar_wait(bar_w[0], ph_w[0], p.error); ph_w[0] ^= 1;
+      mbar_wait(bar_img, ph_img, p.error); ph_img ^= 1;
       tc_fence_after();
 #pragma unroll 4
       for (int ks = 0; ks < 16; ++ks)
@@ -415,14 +439,12 @@ __global__ void __launch_bounds__(kThreads, 2) predict_kernel(const Params p) {
              ks != 0);
       umma_commit(bar_acc);
     }
-    mbar_wait(bar_acc, ph_acc, p.error);
-    ph_acc ^= 1;
-    tc_fence_after();
+    acc_wait(bar_acc, ph_acc, p.error, tid);
     if (tid == 0 && tile + gridDim.x < n_tiles) {  // next tile's LSTM image, behind the softmax
-      mbar_expect_tx(bar_w[0], 10 * kKgB);
-      tma_load(s_w, p.blob + kOffWLstm, 10 * kKgB, bar_w[0]);
+      mbar_expect_tx(bar_img, 10 * kKgB);
+      tma_load(s_w, p.blob + kOffWLstm, 10 * kKgB, bar_img);
     }
-    {
+    if (half == 0) {
       float z[16];
       tmem_ld16(tmem_row, z);
       tmem_ld_wait();

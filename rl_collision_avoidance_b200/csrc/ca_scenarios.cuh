@@ -196,35 +196,18 @@ __global__ void __launch_bounds__(kGenWarps * 32) generate_scenarios_kernel(cons
         const double my_side = side * g_lane;   // side *= 1.01 before every draw
         const double sx = my_side * 2 * rng.u() - my_side, sy = my_side * 2 * rng.u() - my_side;
         const double ex = my_side * 2 * rng.u() - my_side, ey = my_side * 2 * rng.u() - my_side;
-        // cheap tests per lane: spacing to the agents placed so far, start-goal distance
-        const bool cheap = !collides(i, sx, sy, ex, ey) && norm2d(sx - ex, sy - ey) > my_side * 0.5;
-        // "a straight line must NOT already be a solution" (:197-214): the candidate is rejected when EVERY earlier agent
-        // permits a straight-line solution.  The passing candidates are examined in lane order; for each, lane j tests
-        // earlier agent j, so the test is one call deep instead of i calls.
-        unsigned cand = __ballot_sync(0xffffffffu, cheap);
-        int k = -1;
-        while (cand != 0u) {
-          const int kk = __ffs(cand) - 1;
-          bool accept = true;
-          if (i >= 1) {
-            const float csx = (float)bcast_d(sx, kk), csy = (float)bcast_d(sy, kk), cex = (float)bcast_d(ex, kk),
-                        cey = (float)bcast_d(ey, kk);
-            bool permit = true;
-            if (lane < i)
-              permit = permits_straight_line((float)ag.px[lane], (float)ag.py[lane], (float)ag.gx[lane], (float)ag.gy[lane],
-                                             (float)ag.sp[lane], csx, csy, cex, cey, (float)ag.sp[i],
-                                             (float)(ag.rd[lane] + ag.rd[i] + close_range));
-            accept = !__all_sync(0xffffffffu, permit);
-          }
-          if (accept) { k = kk; break; }
-          cand &= cand - 1u;
+        bool ok = !collides(i, sx, sy, ex, ey);
+        if (ok && i >= 1) {  // reject if every earlier agent permits a straight-line solution (no interaction), :197-214
+          bool all_permit = true;
+          for (int j = 0; j < i; ++j)
+            if (!permits_straight_line((float)ag.px[j], (float)ag.py[j], (float)ag.gx[j], (float)ag.gy[j], (float)ag.sp[j],
+                                       (float)sx, (float)sy, (float)ex, (float)ey, (float)ag.sp[i],
+                                       (float)(ag.rd[j] + ag.rd[i] + close_range))) { all_permit = false; break; }
+          ok = !all_permit;
         }
-        if (k >= 0) {
-          if (lane == k) { ag.px[i] = sx; ag.py[i] = sy; ag.gx[i] = ex; ag.gy[i] = ey; }
-          __syncwarp();
-          side *= grow_1p01(k + 1);
-          break;
-        }
+        ok = ok && norm2d(sx - ex, sy - ey) > my_side * 0.5;
+        const int k = commit(i, ok, sx, sy, ex, ey);
+        if (k >= 0) { side *= grow_1p01(k + 1); break; }
         side *= g_round;
       }
     }
