@@ -45,11 +45,10 @@ def run(cls, W, steps, predictor, tf32=False, fixed_agents=False):
     sc = ro.env.scenario_config(cfg.TEST_CASE_ARGS)
     if fixed_agents:   # every world has all A agents (BASELINE configs[2] "10-agent worlds"); policy mix as in training
         sc.min_agents = sc.max_agents = A
+    # every world starts from a scenario of the on-device generator (the training distribution, or all A agents present)
     ro.env.generate_scenarios(sc, 5, only_consumed=False)
-    for _ in range(5):
-        ro.step(); ro.env.generate_scenarios(sc, 5, only_consumed=True); ro.rec.discard()
-    torch.cuda.synchronize()
-    for _ in range(40 if fixed_agents else 0):   # let every world pick up a generated (fixed-size) scenario
+    ro.env.reset(out_obs=ro.rec.obs_slot(ro.t))
+    for _ in range(8):
         ro.step(); ro.env.generate_scenarios(sc, 5, only_consumed=True); ro.rec.discard()
     o = ro.rec.obs_slot(ro.t)   # first use of these torch reductions loads their kernels: keep that out of the timing
     float((o[..., 5] > 0).sum()); float((o[..., 0] != 0).sum())

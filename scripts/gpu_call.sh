@@ -1,6 +1,9 @@
 set -x
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests/test_gpu_predictor.py tests/test_gpu_ga3c.py tests/test_gpu_scenarios.py -m gpu -x -q 2>&1 | tail -25 > gpurun_out/t2.log
-timeout 300 python scripts/predict_probe.py > gpurun_out/predict_probe.log 2>&1
-timeout 300 python scripts/bench_rollout.py --only TrainPhase2:16384:fused:60 --fixed > gpurun_out/rollout.log 2>&1
-tail -5 gpurun_out/t2.log; cat gpurun_out/predict_probe.log gpurun_out/rollout.log
+timeout 600 python scripts/bench_rollout.py --json gpurun_out/rollout.json > gpurun_out/rollout.log 2>&1
+CA_STORE_MODE=vec4 timeout 200 python bench.py --no-cpu-baseline --steps 1200 > gpurun_out/bench_vec4.json 2> gpurun_out/bench_x.err
+CA_ONESHOT_MINBLOCKS=8 timeout 200 python bench.py --no-cpu-baseline --steps 1200 > gpurun_out/bench_mb8.json 2>> gpurun_out/bench_x.err
+CA_ONESHOT_MINBLOCKS=6 timeout 200 python bench.py --no-cpu-baseline --steps 1200 > gpurun_out/bench_mb6.json 2>> gpurun_out/bench_x.err
+CA_DISABLE_L2_PREFETCH=1 timeout 200 python bench.py --no-cpu-baseline --steps 1200 > gpurun_out/bench_nopf.json 2>> gpurun_out/bench_x.err
+CA_DISABLE_PDL=1 timeout 200 python bench.py --no-cpu-baseline --steps 1200 > gpurun_out/bench_nopdl.json 2>> gpurun_out/bench_x.err
+cat gpurun_out/rollout.log; for f in vec4 mb8 mb6 nopf nopdl; do cut -c1-230 gpurun_out/bench_$f.json; done
