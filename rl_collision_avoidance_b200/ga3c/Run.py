@@ -14,6 +14,8 @@ def main():
     from .Server import Server
     out = Server().main(max_seconds=float(os.environ["GA3C_MAX_SECONDS"]) if "GA3C_MAX_SECONDS" in os.environ else None)
     print("all done.", out)
+    if torch.distributed.is_available() and torch.distributed.is_initialized():
+        torch.distributed.destroy_process_group()
 
 
 if __name__ == "__main__":
