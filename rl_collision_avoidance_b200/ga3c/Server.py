@@ -123,6 +123,7 @@ class Server(object):
         self._scenario_cfg = self.rollout.env.scenario_config(cfg.TEST_CASE_ARGS)
         self._scenario_seed = int(seed) * 7919 + 17
         self.rollout.env.generate_scenarios(self._scenario_cfg, self._scenario_seed, only_consumed=False)
+        self.rollout.attach_scenario_generator(self._scenario_cfg, self._scenario_seed)   # refill after every step
         self._pending = []
         self._pending_rows = 0
 
@@ -233,7 +234,6 @@ class Server(object):
                 self._pending.append((x.clone(), r.clone(), a.clone()))
                 self._pending_rows += int(x.shape[0])
             self._train_pending()
-            self.rollout.env.generate_scenarios(self._scenario_cfg, self._scenario_seed, only_consumed=True)
             if steps % refresh_every == 0:
                 s = self.rollout.rec.pop_stats()
                 if self.dist:

@@ -121,6 +121,19 @@ class GpuRollout(object):
         self.env.reset(out_obs=self.rec.obs_slot(0))
         self.last_actions = None
         self.last_values = None
+        self._gen_cfg = None
+        self._gen_done = None
+
+    def attach_scenario_generator(self, scenario_cfg, seed):
+        """After every env step, the worlds that consumed their reset snapshot are handed a fresh test case
+        (ca_generate_scenarios ≙ test_case_fn(**TEST_CASE_ARGS) on env.reset(), collision_avoidance_env.py:283).  The
+        generator runs on a side stream right behind the env step and overlaps the experience bookkeeping of the same
+        step; the next env step waits for it."""
+        torch = self.torch
+        self._gen_cfg, self._gen_seed = scenario_cfg, int(seed)
+        self._gen_stream = torch.cuda.Stream(device=self.device)
+        self._gen_after_step = torch.cuda.Event()
+        self._gen_done = None
 
     def step(self):
         """One env step for every world; returns (reward, done, game_over) device tensors of this step."""
@@ -135,11 +148,24 @@ class GpuRollout(object):
                 actions = torch.argmax(p, dim=1).to(torch.int32)      # ProcessAgent.select_action (:98-103)
             else:
                 actions = torch.multinomial(p, 1, generator=self.gen).squeeze(1).to(torch.int32)
+        main = torch.cuda.current_stream(self.device)
+        if self._gen_done is not None:
+            main.wait_event(self._gen_done)       # the snapshots the step may adopt are complete
         _, reward, done, over = self.env.step(actions.view(self.W, self.A), out_obs=self.rec.obs_slot(self.t + 1))
+        if self._gen_cfg is not None:
+            self._gen_after_step.record(main)
+            self._gen_stream.wait_event(self._gen_after_step)
+            with torch.cuda.stream(self._gen_stream):
+                self.env.generate_scenarios(self._gen_cfg, self._gen_seed, only_consumed=True)
+                if self._gen_done is None:
+                    self._gen_done = torch.cuda.Event()
+                self._gen_done.record(self._gen_stream)
         self.rec.record(self.t, actions, v.contiguous(), reward.view(-1), done.view(-1), over)
         self.last_actions, self.last_values = actions, v
         self.t += 1
         return reward, done, over
 
     def close(self):
+        if self._gen_done is not None:
+            self._gen_done.synchronize()
         self.env.close()

@@ -48,8 +48,9 @@ def run(cls, W, steps, predictor, tf32=False, fixed_agents=False):
     # every world starts from a scenario of the on-device generator (the training distribution, or all A agents present)
     ro.env.generate_scenarios(sc, 5, only_consumed=False)
     ro.env.reset(out_obs=ro.rec.obs_slot(ro.t))
+    ro.attach_scenario_generator(sc, 5)    # consumed worlds get a new scenario after every step (side stream)
     for _ in range(8):
-        ro.step(); ro.env.generate_scenarios(sc, 5, only_consumed=True); ro.rec.discard()
+        ro.step(); ro.rec.discard()
     o = ro.rec.obs_slot(ro.t)   # first use of these torch reductions loads their kernels: keep that out of the timing
     float((o[..., 5] > 0).sum()); float((o[..., 0] != 0).sum())
     torch.cuda.synchronize()
@@ -59,7 +60,6 @@ def run(cls, W, steps, predictor, tf32=False, fixed_agents=False):
     samples = 0
     for k in range(steps):
         ro.step()
-        ro.env.generate_scenarios(sc, 5, only_consumed=True)
         if k % 8 == 7:
             rows += ro.rec.take()[0].shape[0]
             o = ro.rec.obs_slot(ro.t)
@@ -80,6 +80,9 @@ def run(cls, W, steps, predictor, tf32=False, fixed_agents=False):
         t1 = time.perf_counter()
         phases[name] += t1 - t0
         return t1
+    torch.cuda.synchronize()
+    ro._gen_cfg = None          # the breakdown launches the generator itself, on the main stream
+    ro._gen_done = None
     nb = 24
     for k in range(nb):
         t0 = time.perf_counter()

@@ -290,6 +290,39 @@ def test_fused_training_cell_matches_framework_autograd(phase1_cfg, monkeypatch,
         assert float(g0[k].abs().max()) > 0
 
 
+def test_rollout_refreshes_scenarios_on_its_side_stream(phase1_cfg):
+    """GpuRollout.attach_scenario_generator: every new episode of a world starts from a scenario it has not started from
+    before (the refill runs on a side stream between two env steps and must be complete when the next step adopts it)."""
+    import torch
+    from rl_collision_avoidance_b200.ga3c.NetworkVP_rnn import NetworkVP_rnn
+    from rl_collision_avoidance_b200.ga3c.rollout import GpuRollout
+    from rl_collision_avoidance_b200.scenarios import random_worlds
+    cfg = phase1_cfg
+    W, A = 1024, cfg.MAX_NUM_AGENTS_IN_ENVIRONMENT
+    init, nag = random_worlds(W, A, np.random.default_rng(0))
+    ro = GpuRollout(cfg, NetworkVP_rnn("cuda:0", "network", 11, seed=0), W, init, nag, device=0, seed=1)
+    sc = ro.env.scenario_config(cfg.TEST_CASE_ARGS)
+    ro.env.generate_scenarios(sc, 11, only_consumed=False)
+    ro.env.reset(out_obs=ro.rec.obs_slot(ro.t))
+    ro.attach_scenario_generator(sc, 11)
+    last_start = ro.env.get_state()[:, :, :2].copy()
+    same = changed = 0
+    for t in range(120):
+        _, _, over = ro.step()
+        ro.rec.discard()
+        o = over.cpu().numpy().astype(bool)
+        if o.any():
+            st = ro.env.get_state()[:, :, :2]
+            for w in np.nonzero(o)[0]:
+                if np.array_equal(st[w], last_start[w]):
+                    same += 1
+                else:
+                    changed += 1
+                last_start[w] = st[w]
+    assert changed > W // 2 and same == 0, (same, changed)
+    ro.close()
+
+
 def test_server_main_trains(phase1_cfg, tmp_path, monkeypatch):
     monkeypatch.setenv("GA3C_CHECKPOINT_DIR", str(tmp_path))
     from rl_collision_avoidance_b200.ga3c.Server import Server
