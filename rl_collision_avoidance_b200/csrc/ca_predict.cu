@@ -198,12 +198,20 @@ __device__ __forceinline__ void acc_wait(uint32_t bar, uint32_t& phase, int* err
 
 // bias + ReLU + fp16 repack of the thread's accumulator row -> activation buffer (the next product's A operand)
 __device__ __forceinline__ void dense_epilogue(uint32_t tmem_row, const float* bias, uint32_t act_row, int half) {
-#pragma unroll 1
-  for (int c0 = half * (kN / 2); c0 < (half + 1) * (kN / 2); c0 += 32) {
-    float a[32];
-    tmem_ld16(tmem_row + c0, a);
-    tmem_ld16(tmem_row + c0 + 16, a + 16);
+  constexpr int kIters = kN / 2 / 32;   // this thread's 128 columns in blocks of 32, loads one block ahead of the math
+  float buf[2][32];
+  const int cbase = half * (kN / 2);
+  tmem_ld16(tmem_row + cbase, buf[0]);
+  tmem_ld16(tmem_row + cbase + 16, buf[0] + 16);
+#pragma unroll
+  for (int it = 0; it < kIters; ++it) {
+    const int c0 = cbase + it * 32;
+    const float* a = buf[it & 1];
     tmem_ld_wait();
+    if (it + 1 < kIters) {
+      tmem_ld16(tmem_row + c0 + 32, buf[(it + 1) & 1]);
+      tmem_ld16(tmem_row + c0 + 48, buf[(it + 1) & 1] + 16);
+    }
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
       uint32_t w[4];
@@ -328,15 +336,26 @@ __global__ void __launch_bounds__(kThreads, 2) predict_kernel(const Params p) {
       }
       const bool live = t < seq;
       const float* bl = fsec + kFbLstm;
+      // Tensor memory reads are slow (64 B per clock and SM: the 128 KB accumulator of a tile takes ~2000 cycles per step,
+      // as long as its gate math), so the loads of block b + 1 are in flight while block b is evaluated: two register
+      // buffers, tcgen05.wait::ld right before the next block's loads are issued.
+      constexpr int kBlocks = kHid / 2 / 8;
+      float g[2][32];
+      auto load_block = [&](int b, float* dst) {
+        const int u0 = half * (kHid / 2) + b * 8;
+        tmem_ld8(tmem_row + u0, dst);
+        tmem_ld8(tmem_row + 64 + u0, dst + 8);
+        tmem_ld8(tmem_row + 128 + u0, dst + 16);
+        tmem_ld8(tmem_row + 192 + u0, dst + 24);
+      };
+      load_block(0, g[0]);
 #pragma unroll
-      for (int q0 = 0; q0 < kHid / 2; q0 += 8) {
-        const int u0 = half * (kHid / 2) + q0;   // first of 8 units = one k-group of h
-        float gi[8], gj[8], gf[8], go[8];
-        tmem_ld8(tmem_row + u0, gi);
-        tmem_ld8(tmem_row + 64 + u0, gj);
-        tmem_ld8(tmem_row + 128 + u0, gf);
-        tmem_ld8(tmem_row + 192 + u0, go);
+      for (int b = 0; b < kBlocks; ++b) {
+        const int u0 = half * (kHid / 2) + b * 8;   // first of 8 units = one k-group of h
+        const float* gi = g[b & 1];
+        const float *gj = gi + 8, *gf = gi + 16, *go = gi + 24;
         tmem_ld_wait();
+        if (b + 1 < kBlocks) load_block(b + 1, g[(b + 1) & 1]);
         float hn[8];
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
@@ -347,9 +366,9 @@ __global__ void __launch_bounds__(kThreads, 2) predict_kernel(const Params p) {
           const float tj = tanh_fast(gj[q] + bl[64 + u]);
           const float sf = __fmaf_rn(0.5f, tanh_fast(gf[q] + bl[128 + u]), 0.5f);
           const float so = __fmaf_rn(0.5f, tanh_fast(go[q] + bl[192 + u]), 0.5f);
-          const float cn = __fmaf_rn(sf, c[q0 + q], si * tj);
+          const float cn = __fmaf_rn(sf, c[b * 8 + q], si * tj);
           hn[q] = so * tanh_fast(cn);
-          if (live) c[q0 + q] = cn;
+          if (live) c[b * 8 + q] = cn;
         }
         if (live)  // rows whose sequence ended keep c and h
           st_shared_v4(act_row + (u0 / 8) * kKgA, pack_h2_raw(hn[0], hn[1]), pack_h2_raw(hn[2], hn[3]),
