@@ -38,8 +38,8 @@ constexpr int kKgB = kN * 16;      // ... of a 256-row B operand
 constexpr int kKgOut = kOutN * 16; // ... of the 16-row head weights
 
 // ---- packed parameter blob (device memory, written by pack_kernel) -----------------------------------------------------
-constexpr int kOffWLstm = 0;                          // [10][256][8] halfs: k 0..63 = h rows, 64..70 = x rows, rest 0
-constexpr int kOffWL1 = kOffWLstm + 10 * kKgB;        // [10][256][8]: k 0..63 = h rows, 64..67 = host rows, rest 0
+constexpr int kOffWLstm = 0;                          // [10][256][8] halfs: k 0..63 = h rows (x 1/2), 64..70 = x rows, 71 = bias, rest 0
+constexpr int kOffWL1 = kOffWLstm + 10 * kKgB;        // [10][256][8]: k 0..63 = h rows (x 1/2), 64..67 = host rows, rest 0
 constexpr int kOffWL2 = kOffWL1 + 10 * kKgB;          // [32][256][8]
 constexpr int kOffWFc1 = kOffWL2 + 32 * kKgB;         // [32][256][8]
 constexpr int kOffWOut = kOffWFc1 + 32 * kKgB;        // [32][16][8]: n 0..10 logits_p, 11 logits_v, rest 0
@@ -301,7 +301,7 @@ __global__ void __launch_bounds__(kThreads, 2) predict_kernel(const Params p) {
         float x[8];
 #pragma unroll
         for (int k = 0; k < 7; ++k) x[k] = ok ? (o[6 + 7 * t + k] - fsec[kFAvgO + k]) * fsec[kFIstdO + k] : 0.f;
-        x[7] = 0.f;
+        x[7] = ok ? 1.f : 0.f;   // meets the bias row of the packed LSTM kernel: the bias add happens inside the product
         st_shared_v4(act_row + (8 + t) * kKgA, pack_h2(x[0], x[1]), pack_h2(x[2], x[3]), pack_h2(x[4], x[5]),
                      pack_h2(x[6], x[7]));
       }
@@ -335,7 +335,6 @@ __global__ void __launch_bounds__(kThreads, 2) predict_kernel(const Params p) {
         tma_load(s_w, p.blob + kOffWL1, 10 * kKgB, bar_img);
       }
       const bool live = t < seq;
-      const float* bl = fsec + kFbLstm;
       // Tensor memory reads are slow (64 B per clock and SM: the 128 KB accumulator of a tile takes ~2000 cycles per step,
       // as long as its gate math), so the loads of block b + 1 are in flight while block b is evaluated: two register
       // buffers, tcgen05.wait::ld right before the next block's loads are issued.
@@ -359,15 +358,15 @@ __global__ void __launch_bounds__(kThreads, 2) predict_kernel(const Params p) {
         float hn[8];
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
-          const int u = u0 + q;
-          // sigmoid(x) = 0.5 tanh(x / 2) + 0.5: the i, f, o columns of the packed kernel and bias carry the 1/2 (and
-          // the forget bias 1.0), so every gate is one bias add + one tanh.approx
-          const float si = __fmaf_rn(0.5f, tanh_fast(gi[q] + bl[u]), 0.5f);
-          const float tj = tanh_fast(gj[q] + bl[64 + u]);
-          const float sf = __fmaf_rn(0.5f, tanh_fast(gf[q] + bl[128 + u]), 0.5f);
-          const float so = __fmaf_rn(0.5f, tanh_fast(go[q] + bl[192 + u]), 0.5f);
-          const float cn = __fmaf_rn(sf, c[b * 8 + q], si * tj);
-          hn[q] = so * tanh_fast(cn);
+          // sigmoid(x) = 0.5 tanh(x / 2) + 0.5.  The packed kernel carries the 1/2 of the i, f, o columns, the biases (as
+          // the weight row that meets the constant 1 of x_t, forget bias 1.0 included) and a factor 1/2 on the rows that
+          // multiply h, because what is stored as h is 2h:
+          //   c' = sig(f) c + sig(i) tanh(j) = 0.5 [(tf c + c) + (ti tj + tj)],   2 h' = 2 sig(o) tanh(c') = to tc + tc
+          // i.e. 5 tanh.approx + 3 FMA + 1 add + 1 multiply per unit.
+          const float ti = tanh_fast(gi[q]), tj = tanh_fast(gj[q]), tf = tanh_fast(gf[q]), to = tanh_fast(go[q]);
+          const float cn = 0.5f * (__fmaf_rn(tf, c[b * 8 + q], c[b * 8 + q]) + __fmaf_rn(ti, tj, tj));
+          const float tc = tanh_fast(cn);
+          hn[q] = __fmaf_rn(to, tc, tc);
           if (live) c[b * 8 + q] = cn;
         }
         if (live)  // rows whose sequence ended keep c and h
@@ -535,8 +534,9 @@ __global__ void pack_kernel(const PackParams q) {
   if (e < 10 * kN * 8) {  // LSTM kernel [(7 + 64)][256]: TF rows 0..6 = x, 7..70 = h; and layer1 [(4 + 64)][256]
     const int k = (e / (kN * 8)) * 8 + (e & 7), n = (e >> 3) % kN;
     float a = 0.f, b = 0.f;
-    if (k < 64) { a = q.k_lstm[(7 + k) * kN + n]; b = q.k_l1[(4 + k) * kN + n]; }
+    if (k < 64) { a = 0.5f * q.k_lstm[(7 + k) * kN + n]; b = 0.5f * q.k_l1[(4 + k) * kN + n]; }   // rows that meet 2h
     else if (k < 71) { a = q.k_lstm[(k - 64) * kN + n]; if (k < 68) b = q.k_l1[(k - 64) * kN + n]; }
+    else if (k == 71) a = q.b_lstm[n] + ((n >= 128 && n < 192) ? 1.0f : 0.f);   // bias row (forget_bias = 1.0, TF1 LSTMCell)
     if (n < 64 || n >= 128) a *= 0.5f;  // i, f, o gates: sigmoid(x) = 0.5 tanh(x / 2) + 0.5 (gate j = columns 64..127)
     wl[e] = to_h(a);
     w1[e] = to_h(b);
