@@ -89,3 +89,31 @@ def test_server_stats_line_and_save_trigger():
     assert acts.num_actions == 11 and acts.actions.shape == (11, 2)
     np.testing.assert_allclose(acts.actions[:, 0], [1, 1, 1, 1, 1, .5, .5, .5, 0, 0, 0])
     np.testing.assert_allclose(acts.actions[[0, 1, 2, 3, 4], 1], [-np.pi / 6, -np.pi / 12, 0, np.pi / 12, np.pi / 6])
+
+
+def test_bench_workloads_and_reference_arm_line(capsys):
+    """bench.py's workload table (BASELINE configs[1] is the default line; configs[2] env half and configs[3] are extra
+    lines), the live-agent accounting of the ragged workload, and the JSON contract of the --impl reference arm."""
+    import json
+    import types
+    import bench
+    try:
+        bench.select_workload("phase1")
+        assert (bench.AGENTS, bench.WORLDS_PER_GPU, bench.ALG_BYTES_PER_AGENT_STEP) == (4, 65536, 184)
+        assert bench.live_agents(1000) == 4000 and bench.agent_counts(10) is None
+        bench.select_workload("phase2")
+        assert (bench.AGENTS, bench.WORLDS_PER_GPU, bench.ALG_BYTES_PER_AGENT_STEP) == (10, 16384, 352)
+        bench.select_workload("ragged")
+        n = bench.agent_counts(18)
+        assert n.tolist() == [2, 3, 4, 5, 6, 7, 8, 9, 10] * 2 and bench.live_agents(18) == 108   # SURVEY §8(d) config 4
+        assert bench.live_agents(32768) == int((2 + np.arange(32768) % 9).sum())
+        # the reference arm on a reduced world count (the oracle port on the host cores); contract keys of the line
+        bench.WORLDS_PER_GPU = 64
+        bench.run_reference_arm(types.SimpleNamespace(steps=2, warmup=1, gpus=1))
+        line = json.loads(capsys.readouterr().out.strip().splitlines()[-1])
+        assert line["impl"] == "reference" and line["unit"] == "agent-steps/s" and line["higher_is_better"] is True
+        assert line["e2e"] == {"value": line["value"], "unit": "agent-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+        assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1 and line["value"] > 0
+        assert line["config"]["workload"] == bench.WORKLOAD and line["gpu_launches"] == 0
+    finally:
+        bench.select_workload("phase1")
