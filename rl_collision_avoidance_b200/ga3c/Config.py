@@ -94,6 +94,8 @@ class Train(EnvConfig):
         # rows per optimiser step (>= TRAINING_MIN_BATCH_SIZE); 0 = auto: about one step per env step (max(8192, worlds * agents))
         s.GPU_TRAIN_BATCH = int(os.environ.get('GA3C_GPU_TRAIN_BATCH', 0))
         s.GPU_PRINT_EVERY_S = 2.0
+        # trainer matmuls on the tensor cores in TF32 (10-bit significand, fp32 accumulation); off = fp32 like the reference
+        s.GPU_TRAIN_TF32 = int(os.environ.get('GA3C_GPU_TRAIN_TF32', 0))
 
 
 class TrainPhase1(Train):

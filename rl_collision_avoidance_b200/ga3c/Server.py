@@ -88,6 +88,7 @@ class Server(object):
         self.cfg = cfg = cfg or get_config()
         if not torch.cuda.is_available():
             raise RuntimeError("the GPU GA3C loop needs a CUDA device (there is no CPU fallback)")
+        torch.backends.cuda.matmul.allow_tf32 = bool(getattr(cfg, "GPU_TRAIN_TF32", 0))
         self.dist = torch.distributed if (torch.distributed.is_available() and torch.distributed.is_initialized()) else None
         self.rank = self.dist.get_rank() if self.dist else 0
         self.world_size = self.dist.get_world_size() if self.dist else 1

@@ -24,8 +24,9 @@ def rows(cfg, B, rng):
             torch.from_numpy(rng.integers(0, 11, B).astype(np.int64)).cuda())
 
 
-def run(cls, B, fused):
+def run(cls, B, fused, tf32=False):
     os.environ["GA3C_FUSED_TRAIN_CELL"] = "1" if fused else "0"
+    torch.backends.cuda.matmul.allow_tf32 = bool(tf32)
     cfg = getattr(cfgmod, cls)()
     cfgmod.set_config(cfg)
     net = NetworkVP_rnn("cuda:0", "network", 11, seed=0)
@@ -44,11 +45,12 @@ def run(cls, B, fused):
         times.append(e0.elapsed_time(e1) / 4)
     ms = float(np.median(times))
     mem = torch.cuda.max_memory_allocated() / 2 ** 20
-    print("%s B=%d fused_cell=%d: %.3f ms per optimiser step = %.2f M rows/s (peak memory %.0f MiB)" %
-          (cls, B, fused, ms, B / ms / 1e3, mem), flush=True)
+    print("%s B=%d fused_cell=%d tf32_matmul=%d: %.3f ms per optimiser step = %.2f M rows/s (peak memory %.0f MiB)" %
+          (cls, B, fused, tf32, ms, B / ms / 1e3, mem), flush=True)
     cfgmod.set_config(None)
     torch.cuda.reset_peak_memory_stats()
-    return {"config": cls, "batch": B, "fused_cell": bool(fused), "ms_per_step": ms, "rows_per_s": B / ms * 1e3}
+    torch.backends.cuda.matmul.allow_tf32 = False
+    return {"config": cls, "batch": B, "fused_cell": bool(fused), "tf32_matmul": bool(tf32), "ms_per_step": ms, "rows_per_s": B / ms * 1e3}
 
 
 if __name__ == "__main__":
@@ -57,6 +59,7 @@ if __name__ == "__main__":
         for B in (8192, 65536, 262144):
             for fused in (0, 1):
                 out.append(run(cls, B, fused))
+            out.append(run(cls, B, 1, tf32=True))   # GPU_TRAIN_TF32: matmuls on the tensor cores
     if "--json" in sys.argv:
         with open(sys.argv[sys.argv.index("--json") + 1], "w") as f:
             json.dump(out, f, indent=1)

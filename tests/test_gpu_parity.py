@@ -326,19 +326,22 @@ def test_specialised_and_generic_kernels_agree_bitwise(monkeypatch, A, M, sort):
 
 # ----------------------------------------------------------------------------- full-size properties
 
-def _full_size_inputs(W, A, seed):
+def _full_size_inputs(W, A, seed, pattern=False):
     rng = np.random.default_rng(seed)
     side = 3.5 if A <= 4 else 5.0
-    return _random_worlds(rng, W, A, side, policies=(0, 0, 0, 0, 1, 2), ragged=True) + (rng,)
+    init, nag = _random_worlds(rng, W, A, side, policies=(0, 0, 0, 0, 1, 2), ragged=True)
+    if pattern:   # BASELINE configs[3] / SURVEY §8(d) config 4: n_w = 2 + (w mod 9)
+        nag = (2 + np.arange(W) % 9).astype(np.int32)
+    return init, nag, rng
 
 
-@pytest.mark.parametrize("W,A", [(65536, 4), (16384, 10)])
-def test_full_size_world_independence_and_invariants(W, A):
-    """BASELINE configs #2/#3 sizes: a slice of worlds stepped inside the big batch is bit-identical to the same
-    worlds stepped alone (and the alone run is oracle-checked), the run is deterministic, and the flag state
-    machine invariants hold everywhere."""
+@pytest.mark.parametrize("W,A,pattern", [(65536, 4, False), (16384, 10, False), (32768, 10, True)])
+def test_full_size_world_independence_and_invariants(W, A, pattern):
+    """BASELINE configs[1], [2] and [3] sizes (4 x 65 536, 10 x 16 384, ragged 2-10 agents x 32 768): a slice of worlds
+    stepped inside the big batch is bit-identical to the same worlds stepped alone (and the alone run is oracle-checked),
+    the run is deterministic, and the flag state machine invariants hold everywhere."""
     from oracle.ca_oracle import OracleEnv
-    init, nag, rng = _full_size_inputs(W, A, 2024)
+    init, nag, rng = _full_size_inputs(W, A, 2024, pattern)
     T = 24
     acts = rng.choice([0, 1, 2, 2, 2, 3, 4, 6, 9], size=(T, W, A)).astype(np.int32)
     sl = slice(W // 2 - 100, W // 2 + 157)   # 257 worlds straddling CTA boundaries
