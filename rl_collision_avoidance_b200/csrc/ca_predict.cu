@@ -13,9 +13,13 @@
 //     (ca_predictor_pack) so that a chunk of weights is one contiguous TMA bulk copy (cp.async.bulk + mbarrier),
 //   * D = a 128 x 256 fp32 accumulator in tensor memory (256 TMEM columns; two CTAs per SM share the 512),
 // and everything between two products (LSTM gates and state update with the dynamic_rnn sequence mask, bias, ReLU,
-// fp16 repack, softmax, action sampling) happens in the epilogue of the product that feeds it: thread r owns row r
-// (TMEM lane r), reads its accumulator row with tcgen05.ld and writes the next A operand.  Per observation row the
-// kernel reads L floats from HBM and writes 11 + 1 floats (+ 1 int32 action); no intermediate ever leaves the SM.
+// fp16 repack, softmax, action sampling) happens in the epilogue of the product that feeds it: two threads own a row
+// (TMEM lane r; one column half each, 8 warps per tile), read their part of the accumulator row with tcgen05.ld — one
+// block ahead of the math — and write the next A operand.  Two CTAs share an SM, so one tile's products run while the
+// other tile's epilogue keeps the special-function unit busy.  The LSTM biases ride in the product (a weight row that
+// meets a constant-1 input), the 1/2 of sigmoid(x) = 0.5 tanh(x/2) + 0.5 is folded into the packed weights and h is kept
+// doubled, which leaves 5 tanh.approx + 5 arithmetic instructions per unit and step.  Per observation row the kernel
+// reads L floats from HBM and writes 11 + 1 floats (+ 1 int32 action); no intermediate ever leaves the SM.
 // fp16 operands carry an 11-bit significand (the same as TF32) with fp32 accumulation; tests/test_gpu_predictor.py
 // compares against the fp32 PyTorch network with the tolerance stated there.
 #include <cuda_fp16.h>

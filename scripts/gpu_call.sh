@@ -1,5 +1,19 @@
+# The round's evidence run on one B200 (gpurun --timeout 2400 -- 'bash scripts/gpu_call.sh'); outputs land in gpurun_out/ and
+# are copied / summarised into profiles/ (see profiles/README.md).
 set -x
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "full_size" 2>&1 | tail -4 > gpurun_out/t2.log
+python __graft_entry__.py smoke > gpurun_out/smoke.log 2>&1
+timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -8 > gpurun_out/t2.log
+timeout 300 python bench.py > gpurun_out/bench_a.json 2> gpurun_out/bench_a.err
+timeout 300 python bench.py --impl reference --steps 30 --warmup 3 > gpurun_out/bench_ref.json 2>> gpurun_out/bench_a.err
+timeout 300 python bench.py --steps 1200 --workload phase2 > gpurun_out/bench_phase2.json 2>> gpurun_out/bench_a.err
+timeout 300 python bench.py --steps 1200 --workload ragged > gpurun_out/bench_ragged.json 2>> gpurun_out/bench_a.err
+timeout 600 python scripts/bench_rollout.py --json gpurun_out/rollout.json > gpurun_out/rollout.log 2>&1
 timeout 600 python scripts/bench_trainer.py --json gpurun_out/trainer.json > gpurun_out/trainer.log 2>&1
-tail -3 gpurun_out/t2.log; cat gpurun_out/trainer.log
+timeout 300 python scripts/predict_probe.py > gpurun_out/predict_probe.log 2>&1
+./build/mufu_probe > gpurun_out/mufu_probe.log 2>&1
+timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -s 60 -c 120 --csv --log-file gpurun_out/launches_bench.csv python bench.py --steps 96 --warmup 12 --no-cpu-baseline > gpurun_out/ncu_launches.log 2>&1
+timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --csv --log-file gpurun_out/launches_rollout.csv python scripts/bench_rollout.py --only TrainPhase2:16384:fused:24 --fixed > gpurun_out/ncu_rollout.log 2>&1
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:ca_step_kernel -s 30 -c 2 -o gpurun_out/prof_step -f python bench.py --steps 48 --warmup 12 --no-cpu-baseline > gpurun_out/ncu_step.log 2>&1
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:predict_kernel -s 2 -c 1 -o gpurun_out/prof_predict -f python scripts/predict_probe.py one 9 163840 0 > gpurun_out/ncu_predict.log 2>&1
+tail -2 gpurun_out/smoke.log; tail -3 gpurun_out/t2.log; cut -c1-200 gpurun_out/bench_a.json; cat gpurun_out/rollout.log
