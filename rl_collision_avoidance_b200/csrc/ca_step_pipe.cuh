@@ -1,4 +1,5 @@
-// ca_step_pipe.cuh — persistent, software-pipelined step kernel (the default for A in {2,3,4,5,6,8,10}).
+// ca_step_pipe.cuh — persistent, software-pipelined step kernel (CA_STEP_KERNEL=pipe; the one-shot kernel of
+// ca_step_fast.cuh is the default and shares this file's pair pass and row assembly).
 //
 // Same arithmetic as ca_world_kernel<true> / ca_step_kernel<kA> (bitwise-identical outputs, see
 // tests/test_gpu_parity.py::test_specialised_and_generic_kernels_agree_bitwise); what changes is how the data

@@ -4,11 +4,12 @@ Replaces, for W worlds at once:
   ProcessAgent.run_episode / predict / select_action / _accumulate_rewards   GA3C/ProcessAgent.py:54-211
   ThreadPredictor.run (dynamic batching of <=128 requests)                    GA3C/ThreadPredictor.py:40-75
   Environment (VecEnv adapter, previous_state/current_state)                  GA3C/Environment.py:37-116
-Every env step is: one batched NetworkVP forward over all agent slots -> on-device multinomial sampling
-(argmax in PLAY/EVALUATE mode) -> one fused env.step launch that writes the next observation straight into the
-rollout's observation ring -> one bookkeeping launch (ca_ga3c_record) that appends the experience of every
-learning agent and emits the training rows (x_, r_, a_) the reference's generator would yield at this step.
-Nothing leaves the GPU; torch is the allocator / stream / network library.
+Every env step is: the row plan of the learning agents (ca_predict_plan) -> ONE fused predictor launch (NetworkVP forward +
+action sampling, argmax in PLAY/EVALUATE mode; ca_predict_rows) -> one fused env.step launch that writes the next
+observation straight into the rollout's observation ring -> the bookkeeping launches (ca_ga3c_record: experience lists,
+n-step returns, then the row gather) that emit the training rows (x_, r_, a_) the reference's generator would yield at
+this step; the scenario refresh of the worlds that just reset runs on a side stream behind the env step.
+Nothing leaves the GPU; torch is the allocator / stream library (and the network under GA3C_PREDICTOR=composed).
 """
 import ctypes as C
 

@@ -6,9 +6,9 @@ gen_rand_testcases.py:137-226 generate_rand_case): radius ~ U[radius_bnds], pref
 U[speed_bnds] draws, start/goal ~ U[-side, side]^2 with the side growing 1% per rejected draw,
 rejection of starts/goals closer than r_i + r_j + GETTING_CLOSE_RANGE to an earlier agent's, and
 |start - goal| > side/2; heading ~ U(-pi, pi) (test_cases.py:315); side length by agent count
-(GCA/envs/config.py:57-60).  Distributional parity only: the swap/circle cases (15 % each) and the
-"straight line must not already be a solution" rejection of the reference are not reproduced yet
-(SURVEY.md §8 f-1, next row).
+(GCA/envs/config.py:57-60).  Distributional parity only, and a subset: the swap/circle cases (15 % each) and the
+"straight line must not already be a solution" rejection of the reference are reproduced by the ON-DEVICE generator
+(csrc/ca_scenarios.cuh, ca_generate_scenarios — what training uses for every episode after the first), not here.
 """
 import numpy as np
 
