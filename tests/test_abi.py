@@ -56,6 +56,32 @@ def test_config_struct_layout_matches_c(tmp_path):
     assert (a, b, c) == (_abi.INIT_STRIDE, _abi.STATE_STRIDE, _abi.obs_len(3))
 
 
+def test_other_struct_layouts_and_constants_match_c(tmp_path):
+    """ca_ga3c_buffers, ca_predictor_params, ca_scenario_config and the predictor constants: the ctypes mirrors in _abi.py
+    have the sizes, field offsets and values the C header gives them (compiled with gcc, no GPU needed)."""
+    structs = [("ca_ga3c_buffers", _abi.CaGa3cBuffers), ("ca_predictor_params", _abi.CaPredictorParams),
+               ("ca_scenario_config", _abi.CaScenarioConfig)]
+    prog = ["#include <stdio.h>", "#include <stddef.h>", '#include "ca_step.h"', "int main(void){"]
+    for cname, mirror in structs:
+        prog.append('printf("%%zu\\n", sizeof(%s));' % cname)
+        prog += ['printf("%%zu\\n", offsetof(%s, %s));' % (cname, f[0]) for f in mirror._fields_]
+    prog += ['printf("%d %d %d\\n", (int)CA_PREDICTOR_BLOB_BYTES, (int)CA_PREDICT_PLAN_COUNTERS, (int)CA_MAX_AGENTS);', "return 0;}"]
+    src = tmp_path / "probe2.c"
+    src.write_text("\n".join(prog))
+    exe = tmp_path / "probe2"
+    subprocess.check_call(["gcc", "-I", os.path.join(REPO, "include"), "-o", str(exe), str(src)])
+    lines = subprocess.check_output([str(exe)], text=True).split("\n")
+    k = 0
+    for cname, mirror in structs:
+        assert int(lines[k]) == C.sizeof(mirror), cname
+        k += 1
+        for f in mirror._fields_:
+            assert int(lines[k]) == getattr(mirror, f[0]).offset, (cname, f[0])
+            k += 1
+    blob, counters, max_agents = (int(x) for x in lines[k].split())
+    assert blob == _abi.CA_PREDICTOR_BLOB_BYTES and counters == _abi.CA_PREDICT_PLAN_COUNTERS and max_agents == 32
+
+
 def test_default_config_matches_python_mirror(built_lib):
     c1 = _abi.CaConfig()
     assert built_lib.ca_default_config(C.byref(c1), 7, 4) == 0
