@@ -40,6 +40,59 @@ def forward(variables, x, avg, std, M, host_len=4, other_len=7, first=1, min_pol
     return p, v
 
 
+def _h(a):
+    """round to fp16 and back (what an operand of the fused predictor's tensor-core products carries)"""
+    return np.asarray(a, dtype=np.float32).astype(np.float16).astype(np.float64)
+
+
+def forward_fp16_operands(variables, x, avg, std, M, host_len=4, other_len=7, first=1, min_policy=0.0, tanh_rel_err=0.0,
+                          rng=None):
+    """The same network with the ARITHMETIC of the fused predictor kernel (csrc/ca_predict.cu): every operand of a matrix
+    product — weights, the normalised inputs, h, the ReLU activations, and the LSTM bias, which rides in the product as a
+    weight row — is rounded to fp16; products accumulate in (at least) fp32; dense biases, gates and the softmax are fp32.
+    tanh_rel_err > 0 additionally perturbs every tanh by a random relative error of that size (tanh.approx: 2^-11).
+    Not bit-exact with the kernel (accumulation order, the hardware's tanh), but it carries the same rounding sources, so
+    its distance from `forward` is the error the kernel is expected to have against the fp32 network."""
+    x = np.asarray(x, dtype=np.float64)
+    xn = (x - avg) / std
+    seq_len = x[:, 0]
+    host = _h(xn[:, first:first + host_len])
+    others = _h(xn[:, first + host_len:].reshape(-1, M, other_len))
+    B, H = x.shape[0], 64
+    K = _h(variables["rnn/lstm_cell/kernel"])
+    bias = variables["rnn/lstm_cell/bias"].astype(np.float64).copy()
+    bias[2 * H:3 * H] += 1.0                      # forget_bias folded into the packed bias row
+    b = _h(bias)
+
+    def tanh(z):
+        t = np.tanh(z)
+        if tanh_rel_err > 0.0:
+            t = t * (1.0 + tanh_rel_err * (rng or np.random.default_rng(0)).uniform(-1, 1, size=t.shape))
+        return t
+
+    def sig(z):                                    # 0.5 tanh(z / 2) + 0.5 as the kernel evaluates it
+        return 0.5 * tanh(0.5 * z) + 0.5
+
+    h = np.zeros((B, H)); c = np.zeros((B, H))
+    for t in range(M):
+        z = np.concatenate([others[:, t], _h(h)], axis=1) @ K + b
+        i, j, f, o = np.split(z, 4, axis=1)
+        c_new = sig(f) * c + sig(i) * tanh(j)
+        h_new = sig(o) * tanh(c_new)
+        live = (seq_len > t)[:, None]
+        c = np.where(live, c_new, c)
+        h = np.where(live, h_new, h)
+    a = np.concatenate([host, _h(h)], axis=1)
+    for name in ("layer1", "layer2", "fullyconnected1"):
+        a = _h(np.maximum(a @ _h(variables[name + "/kernel"]) + variables[name + "/bias"], 0.0))
+    logits = a @ _h(variables["logits_p/kernel"]) + variables["logits_p/bias"]
+    v = (a @ _h(variables["logits_v/kernel"]) + variables["logits_v/bias"])[:, 0]
+    e = np.exp(logits - logits.max(axis=1, keepdims=True))
+    p = e / e.sum(axis=1, keepdims=True)
+    p = (p + min_policy) / (1.0 + min_policy * p.shape[1])
+    return p, v
+
+
 def a3c_costs(p, v, y_r, a_onehot, beta, log_epsilon=1e-6):
     """NetworkVPCore.py:71-98 (sums, not means)."""
     sel = (p * a_onehot).sum(axis=1)
