@@ -262,7 +262,7 @@ def run_ours(args):
     gen = torch.Generator(device="cuda")
     gen.manual_seed(1234 + rank)
     actions = [torch.randint(0, 11, (W, A), dtype=torch.int32, device="cuda", generator=gen) for _ in range(T)]
-    bytes_per_set = 2 * (W // max(1, min(32 // A, 16))) * 2688 + W * A * 4 + W * A * _abi.obs_len(OTHERS) * 4 + W * A * 9   # state blocks x2, actions, obs, outputs
+    bytes_per_set = 2 * (W // max(1, min(32 // A, 16))) * 2304 + W * A * 4 + W * A * _abi.obs_len(OTHERS) * 4 + W * A * 9   # state blocks x2, actions, obs, outputs
 
     def eager_step(k):
         envs[k % R].step(actions[k % T])

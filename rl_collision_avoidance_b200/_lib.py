@@ -14,7 +14,7 @@ CSRC_DIR = os.path.join(PKG_DIR, "csrc")
 LIB_PATH = os.path.join(PKG_DIR, "libcastep.so")
 SOURCES = ["ca_step.cu", "ca_predict.cu"]
 OBJ_DIR = os.path.join(CSRC_DIR, "_obj")
-HEADERS = [os.path.join(CSRC_DIR, "ca_kernels.cuh"), os.path.join(CSRC_DIR, "ca_step_fast.cuh"), os.path.join(CSRC_DIR, "ca_step_pipe.cuh"), os.path.join(CSRC_DIR, "ca_ga3c.cuh"), os.path.join(CSRC_DIR, "ca_scenarios.cuh"), os.path.join(PKG_DIR, "..", "include", "ca_step.h")]
+HEADERS = [os.path.join(CSRC_DIR, "ca_kernels.cuh"), os.path.join(CSRC_DIR, "ca_step_fast.cuh"), os.path.join(CSRC_DIR, "ca_step_stream.cuh"), os.path.join(CSRC_DIR, "ca_ga3c.cuh"), os.path.join(CSRC_DIR, "ca_scenarios.cuh"), os.path.join(PKG_DIR, "..", "include", "ca_step.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",  # B200 only

@@ -20,34 +20,34 @@
 #include <stdint.h>
 
 #include "../../include/ca_step.h"
+#include "ca_math.cuh"
 
 namespace ca {
 
 constexpr int kBlock = 128;           // threads per CTA
 constexpr int kWarps = kBlock / 32;   // warps per CTA
 constexpr unsigned kFull = 0xffffffffu;
-constexpr double kPi = 3.141592653589793;  // np.pi
 
 // ---- state layout in HBM: chunk-major AoSoA --------------------------------------------------------------------------
 // A "chunk" is what one warp processes: wpw = min(32 / A, 16) whole worlds = wpw * A (<= 32) agent slots, one per lane.
-// All state of a chunk lives in ONE contiguous, 128-byte aligned block of kBlkBytes = 2688 bytes:
-//     double field[8][32]            px py heading time_remaining gx gy radius pref_speed   (what a step reads)
+// All state of a chunk lives in ONE contiguous, 128-byte aligned block of kBlkBytes = 2304 bytes:
+//     double field[8][32]            px py heading time_remaining | gx gy radius pref_speed
 //     uint8  flags[32], policy[32]   per lane
 //     int32  num_agents[16]          per world of the chunk
-//     double vx[32], vy[32]          velocity (written by a step, read only by reset / get_state)
-// so a warp reads/writes each field as one coalesced 256-byte run at a constant offset from a single base pointer, and
-// a chunk's entire state can be fetched with a single TMA bulk copy (ca_step_pipe.cuh).  The reset snapshot uses the
-// same layout in a second buffer.
-// Order inside the block (offsets in doubles): the eight fields a step READS, then the byte/int tail, then the two
-// velocity fields, which a step only writes (it overwrites them before any use) — so the part of a block that a step
-// has to fetch is its first kBlkReadBytes = 2176 bytes.
-constexpr int kFields = 10;
+//     float  speed[32]               the float32 speed command the agent last executed (0 once it is done)
+// so a warp reads/writes each field as one coalesced run at a constant offset from a single base pointer, and the part
+// of a block that a step has to fetch (everything but `speed`) is ONE TMA bulk copy of kBlkReadBytes = 2176 bytes
+// (ca_step_stream.cuh).  The reset snapshot uses the same layout in a second buffer.
+// The velocity is not stored: a step writes it as speed * (cos h, sin h) with h the heading it also writes
+// (UnicycleDynamics.step, dynamics/UnicycleDynamics.py:33-34), so the 4-byte command reproduces both float64 components
+// bit for bit (ca_get_state, first observation after a partial reset) and a step moves 12 bytes less per agent.
+constexpr int kFields = 8;
 constexpr int O_PX = 0, O_PY = 32, O_HD = 64, O_TR = 96, O_GX = 128, O_GY = 160, O_RAD = 192, O_PS = 224;
 constexpr int O_TAIL = 256;                     // flags[32] u8, policy[32] u8, num_agents[16] i32
-constexpr int O_VX = 272, O_VY = 304;
-constexpr int kBlkDoubles = kFields * 32 + 16;  // 336 doubles
-constexpr int kBlkBytes = kBlkDoubles * 8;      // 2688 bytes
-constexpr int kBlkReadBytes = O_VX * 8;         // 2176 bytes: everything except vx, vy
+constexpr int O_SPD = 272;                      // float[32]
+constexpr int kBlkDoubles = kFields * 32 + 16 + 16;  // 288 doubles
+constexpr int kBlkBytes = kBlkDoubles * 8;      // 2304 bytes
+constexpr int kBlkReadBytes = O_SPD * 8;        // 2176 bytes: everything except the speed command
 
 struct StateBlocks {
   double* base;  // [n_chunks][kBlkDoubles]
@@ -59,6 +59,7 @@ __device__ __forceinline__ double* blk_ptr(const StateBlocks& s, long chunk) { r
 __device__ __forceinline__ uint8_t* blk_flags(double* blk) { return reinterpret_cast<uint8_t*>(blk + O_TAIL); }
 __device__ __forceinline__ uint8_t* blk_policy(double* blk) { return reinterpret_cast<uint8_t*>(blk + O_TAIL) + 32; }
 __device__ __forceinline__ int32_t* blk_nag(double* blk) { return reinterpret_cast<int32_t*>(blk + O_TAIL + 8); }
+__device__ __forceinline__ float* blk_spd(double* blk) { return reinterpret_cast<float*>(blk + O_SPD); }
 
 // (world, agent) -> (chunk, lane) for kernels that are not organised warp-per-chunk
 __device__ __forceinline__ void slot_of(int w, int i, int A, long& chunk, int& lane, int& wl) {
@@ -75,6 +76,8 @@ struct Params {
   int use_bulk_store;   // 1: TMA bulk store of full tiles
   int warp_store;       // specialised kernel: each warp stores its own rows (warp tile is a multiple of 16 B)
   int prefetch_chunks;  // one-shot kernel: L2-prefetch the state block of chunk + prefetch_chunks (0 = off)
+  int dynamic_sched;    // streaming kernel: 1 = warps pull chunks from *ticket, 0 = strided static schedule
+  unsigned* ticket;     // streaming kernel: self-resetting work counter (one per env handle)
   double dt, thr_sq, close_range, r_goal, r_coll, r_step, r_min, r_max, max_heading_change, sensing_horizon;
   StateBlocks s;        // live state (agent counts inside the blocks)
   StateBlocks s0;       // snapshot injected by ca_set_world_state / ca_set_reset_state / the generator (for reset)
@@ -96,14 +99,6 @@ __constant__ double kActDhead[11] = {-0x1.0c152382d7365p-1, -0x1.0c152382d7365p-
                                      0x1.0c152382d7365p-1,  -0x1.0c152382d7365p-1, 0.0, 0x1.0c152382d7365p-1,
                                      -0x1.0c152382d7365p-1, 0.0,                   0x1.0c152382d7365p-1};
 
-// GCA/envs/util.py:132-137 (same loops; non-finite input is left alone instead of spinning forever)
-__device__ __forceinline__ double wrap_angle(double a) {
-  if (!isfinite(a)) return a;
-  while (a >= kPi) a -= 2 * kPi;
-  while (a < -kPi) a += 2 * kPi;
-  return a;
-}
-
 // np.dot on 2-vectors as NumPy/OpenBLAS evaluates it: fma(a1, b1, a0*b0) (see oracle/ca_oracle.c np_dot2)
 __device__ __forceinline__ double dot2(double a0, double a1, double b0, double b1) {
   return __fma_rn(a1, b1, __dmul_rn(a0, b0));
@@ -114,13 +109,15 @@ struct Ego {
   float hego;             // heading_ego_frame as it goes into the float32 observation
 };
 
-// Agent.get_ref (GCA/envs/agent.py:326-346): distance to goal and the ego-frame axes, float64.
+// Agent.get_ref (GCA/envs/agent.py:326-346): distance to goal and the ego-frame axes, float64.  The two divisions by
+// the same distance share one refined reciprocal (ca_math.cuh: same correctly rounded quotients as two IEEE divisions).
 __device__ __forceinline__ void ego_axes(double px, double py, double gx, double gy, Ego& e) {
   const double dx = gx - px, dy = gy - py;
   e.dist = sqrt(dx * dx + dy * dy);
   if (e.dist > 1e-8) {
-    e.prx = dx / e.dist;
-    e.pry = dy / e.dist;
+    const double r = recip_refined(e.dist);
+    e.prx = div_by(dx, e.dist, r);
+    e.pry = div_by(dy, e.dist, r);
   } else {
     e.prx = dx;
     e.pry = dy;
@@ -134,14 +131,23 @@ __device__ __forceinline__ double heading_ego_exact(const Ego& e, double hd) {
 }
 
 // The same quantity for the observation vector.  Observations are float32 (tolerance 1e-5); nothing downstream of
-// the env reads it back, so it is evaluated with the float32 atan2 (|error| < 1e-6 rad) which is ~4x cheaper than the
-// float64 one and sits at the end of the kernel's longest dependency chain.
+// the env reads it back, so it is evaluated with a branch-free float32 atan2 (|error| < 1e-6 rad) which is several
+// times cheaper than the float64 one and sits at the end of the kernel's longest dependency chain.
 __device__ __forceinline__ float heading_ego_obs(const Ego& e, double hd) {
   const float pi = 3.14159265358979323846f;
-  float a = (float)hd - atan2f((float)e.pry, (float)e.prx);
+  float a = (float)hd - atan2f_obs((float)e.pry, (float)e.prx);
   if (a >= pi) a -= 2.f * pi;
   if (a < -pi) a += 2.f * pi;
   return a;
+}
+
+// Observation-only projections (float32 outputs, 1e-5 tolerance; no decision reads them).  One definition for every
+// kernel so that they agree bit for bit.  p_parallel as the reference evaluates it (np.dot in float64), then rounded.
+__device__ __forceinline__ float obs_pprl(double rx, double ry, const Ego& e) { return (float)dot2(rx, ry, e.prx, e.pry); }
+// velocity of the other agent in the ego frame, from its float32 velocity
+__device__ __forceinline__ void obs_vel(float vxj, float vyj, float prxf, float pryf, float& vprl, float& vorth) {
+  vprl = fmaf(vyj, pryf, vxj * prxf);
+  vorth = fmaf(vyj, prxf, -(vxj * pryf));
 }
 
 __device__ __forceinline__ Ego ego_frame(double px, double py, double gx, double gy, double hd) {
@@ -219,27 +225,41 @@ __device__ __forceinline__ bool key_before(int mode, double qa, double pa, doubl
 // The per-lane agent record kept in registers.
 struct Agent {
   double px, py, hd, vx, vy, tr, gx, gy, rad, ps;
+  float spd;  // float32 speed command last executed (what the block stores instead of the velocity)
   unsigned flags;
   int policy;
 };
 
-// kVel = false: the caller overwrites vx, vy before using them (every step kernel does: a moving agent gets its new
-// velocity, a finished one zero), so they are not fetched.
+// kVel = true: the velocity is rebuilt from the stored float32 speed command and the heading exactly as the step
+// that produced them wrote it (speed * cos h, speed * sin h with the same sincos).  kVel = false: the caller
+// overwrites vx, vy before using them (every step kernel does: a moving agent gets its new velocity, a finished one
+// zero), so neither the command nor the trigonometry is needed.
 template <bool kVel = true>
 __device__ __forceinline__ void load_agent(const double* blk, int lane, Agent& a) {
   a.px = blk[O_PX + lane]; a.py = blk[O_PY + lane]; a.hd = blk[O_HD + lane];
-  if (kVel) { a.vx = blk[O_VX + lane]; a.vy = blk[O_VY + lane]; } else { a.vx = 0.0; a.vy = 0.0; }
   a.tr = blk[O_TR + lane];
   a.gx = blk[O_GX + lane]; a.gy = blk[O_GY + lane]; a.rad = blk[O_RAD + lane];
   a.ps = blk[O_PS + lane];
   a.flags = blk_flags(const_cast<double*>(blk))[lane];
   a.policy = blk_policy(const_cast<double*>(blk))[lane];
+  if (kVel) {
+    a.spd = blk_spd(const_cast<double*>(blk))[lane];
+    a.vx = 0.0; a.vy = 0.0;
+    if (a.spd != 0.f) {  // the agent has moved: its heading is a wrapped angle and this is the step's own expression
+      double sh, ch;
+      sincos_wrapped(a.hd, sh, ch);
+      a.vx = (double)a.spd * ch; a.vy = (double)a.spd * sh;
+    }
+  } else {
+    a.spd = 0.f; a.vx = 0.0; a.vy = 0.0;
+  }
 }
 
 // write-back of one lane: the dynamic fields always, goal / static fields only when they changed
 __device__ __forceinline__ void store_agent(double* blk, int lane, const Agent& a, bool goal_too, bool all) {
   blk[O_PX + lane] = a.px; blk[O_PY + lane] = a.py; blk[O_HD + lane] = a.hd;
-  blk[O_VX + lane] = a.vx; blk[O_VY + lane] = a.vy; blk[O_TR + lane] = a.tr;
+  blk[O_TR + lane] = a.tr;
+  blk_spd(blk)[lane] = a.spd;
   blk_flags(blk)[lane] = (uint8_t)a.flags;
   if (goal_too || all) { blk[O_GX + lane] = a.gx; blk[O_GY + lane] = a.gy; }
   if (all) { blk[O_RAD + lane] = a.rad; blk[O_PS + lane] = a.ps; blk_policy(blk)[lane] = (uint8_t)a.policy; }
@@ -247,7 +267,96 @@ __device__ __forceinline__ void store_agent(double* blk, int lane, const Agent& 
 
 __device__ __forceinline__ void zero_agent(Agent& a) {
   a.px = a.py = a.hd = a.vx = a.vy = a.tr = a.gx = a.gy = a.rad = a.ps = 0.0;
-  a.flags = 0; a.policy = 0;
+  a.spd = 0.f; a.flags = 0; a.policy = 0;
+}
+
+// ---- the step body shared by every step kernel (generic, one-shot, streaming) ------------------------------------------
+// _take_action (collision_avoidance_env.py:217-252): every agent picks its float32 command from the pre-step state
+// (LearningPolicyGA3C.py:13-27 + action table, LearningPolicy.py:13-33, NonCooperativePolicy.py:9-22,
+// StaticPolicy.py:9-23), then all agents move (Agent.take_action agent.py:190-238, UnicycleDynamics.step
+// dynamics/UnicycleDynamics.py:14-47, _check_if_at_goal agent.py:148-151, time budget agent.py:232-236).
+// `act` is the lane's discrete action, `g` its flat (world, agent) index (continuous actions are read from p.cont).
+__device__ __forceinline__ void step_take_action(const Params& p, Agent& a, int act, size_t g, bool valid) {
+  const bool was_done = (a.flags & CA_F_DONE_MASK) != 0;
+  float cmd_speed = 0.f, cmd_dh = 0.f;  // all_actions is float32 (:238)
+  if (valid && !was_done) {
+    if (a.policy == CA_POLICY_NONCOOP) {
+      // reads the ego heading of the pre-step state; it feeds the dynamics, so float64 atan2
+      Ego e0;
+      ego_axes(a.px, a.py, a.gx, a.gy, e0);
+      cmd_speed = (float)a.ps;
+      cmd_dh = (float)(-heading_ego_exact(e0, a.hd));
+    } else if (a.policy == CA_POLICY_LEARNING_GA3C) {
+      const int k = act < 0 ? 0 : (act > 10 ? 10 : act);
+      cmd_speed = (float)(a.ps * kActSpeed[k]);
+      cmd_dh = (float)kActDhead[k];
+    } else if (a.policy == CA_POLICY_LEARNING) {
+      double e0 = 0.0, e1 = 0.5;
+      if (p.cont) { e0 = p.cont[2 * g]; e1 = p.cont[2 * g + 1]; }
+      cmd_speed = (float)(a.ps * e0);
+      cmd_dh = (float)(p.max_heading_change * (2. * e1 - 1.));
+    } else if (a.policy == CA_POLICY_STATIC) {  // goal := pos
+      a.gx = a.px;
+      a.gy = a.py;
+    }
+  }
+  if (!valid) return;
+  if (was_done) {
+    if (a.flags & CA_F_AT_GOAL) a.flags |= CA_F_WAS_AT_GOAL;
+    if (a.flags & CA_F_IN_COLLISION) a.flags |= CA_F_WAS_IN_COLLISION;
+    a.vx = 0.0;
+    a.vy = 0.0;
+    a.spd = 0.f;
+  } else {
+    const double speed = (double)cmd_speed;
+    const double h = wrap_angle((double)cmd_dh + a.hd);
+    double sh, ch;
+    sincos_wrapped(h, sh, ch);
+    a.px += speed * ch * p.dt;
+    a.py += speed * sh * p.dt;
+    a.vx = speed * ch;
+    a.vy = speed * sh;
+    a.spd = cmd_speed;
+    a.hd = h;
+    const double ex = a.px - a.gx, ey = a.py - a.gy;
+    if (ex * ex + ey * ey <= p.thr_sq) a.flags |= CA_F_AT_GOAL; else a.flags &= ~CA_F_AT_GOAL;
+    a.tr -= p.dt;
+    if (a.tr <= 0.0) a.flags |= CA_F_RAN_OUT_OF_TIME;
+  }
+}
+
+// _compute_rewards (:319-368; sets in_collision) and _check_which_agents_done (:411-439) for one lane, given the result
+// of the all-pairs pass.  gmask = the lanes of this lane's world.  Returns the reward; dn = agent done, over = game_over.
+__device__ __forceinline__ float step_reward_done(const Params& p, Agent& a, bool valid, int i, bool coll, double nearest,
+                                                  unsigned gmask, bool& dn, bool& over) {
+  // float32 is what leaves the kernel; rounding is monotone, so clipping after the rounding gives the same float as
+  // clipping the float64 value first (np.clip at :364) and rounding then
+  float r = (float)p.r_step;
+  if (valid) {
+    if (a.flags & CA_F_AT_GOAL) {
+      if (!(a.flags & CA_F_WAS_AT_GOAL)) r = (float)p.r_goal;  // goal beats collision; in_collision is not set
+    } else if (!(a.flags & CA_F_WAS_IN_COLLISION)) {
+      if (coll) {
+        r = (float)p.r_coll;
+        a.flags |= CA_F_IN_COLLISION;
+      } else if (nearest <= p.close_range) {
+        r = (float)(-0.1 - nearest / 2.);
+      }
+    }
+    r = fminf(fmaxf(r, (float)p.r_min), (float)p.r_max);
+    if (p.over_mode == CA_OVER_FIRST_AGENT_DONE && i > 0) r = 0.f;  // rewards = rewards[0] (:365-366)
+  } else {
+    r = 0.f;
+  }
+  dn = valid ? (a.flags & CA_F_DONE_MASK) != 0 : true;
+  const bool learning = valid && (a.policy == CA_POLICY_LEARNING_GA3C || a.policy == CA_POLICY_LEARNING);
+  bool blocks_over;  // this agent keeps the episode alive
+  if (p.over_mode == CA_OVER_ALL_DONE) blocks_over = valid && !dn;
+  else if (p.over_mode == CA_OVER_FIRST_AGENT_DONE) blocks_over = valid && i == 0 && !dn;
+  else blocks_over = learning && !dn;
+  const unsigned alive = __ballot_sync(kFull, blocks_over) & gmask;
+  over = alive == 0u;
+  return r;
 }
 
 // Shared-memory carve-up of one CTA.
@@ -354,15 +463,14 @@ __device__ __forceinline__ void write_obs_row(const Params& p, const Smem& sm, c
       const int ak = k * kBlock + tid;
       slot += key_before(mode2, sm.kq[ak], sm.kp[ak], tti ? sm.kt[ak] : 0.0, k, qj, pj, tj, j) ? 1 : 0;
     }
-    // observation-only projections are evaluated in float32 from the rounded float64 inputs (same formulas as
-    // pipe_write_obs_row, so that all step kernels agree bit for bit); p_orth is the float64 tie-break key
-    const float rxf = (float)(xj - a.px), ryf = (float)(yj - a.py), prxf = (float)e.prx, pryf = (float)e.pry;
-    const float vxf = (float)vxj, vyf = (float)vyj, rjf = (float)rj, raf = (float)a.rad;
+    // observation-only projections: shared definitions (obs_pprl / obs_vel), so that all step kernels agree bit for
+    // bit; p_orth is the float64 tie-break key
+    const float prxf = (float)e.prx, pryf = (float)e.pry;
+    const float rjf = (float)rj, raf = (float)a.rad;
     float* s = row + CA_OBS_HOST_LEN + CA_OBS_OTHER_LEN * slot;
-    s[0] = fmaf(ryf, pryf, rxf * prxf);
+    s[0] = obs_pprl(xj - a.px, yj - a.py, e);
     s[1] = (float)pj;
-    s[2] = fmaf(vyf, pryf, vxf * prxf);
-    s[3] = fmaf(vyf, prxf, -(vxf * pryf));
+    obs_vel((float)vxj, (float)vyj, prxf, pryf, s[2], s[3]);
     s[4] = rjf;
     s[5] = raf + rjf;
     s[6] = (float)(sm.kd[aj] - a.rad - rj);
@@ -432,61 +540,10 @@ __global__ void __launch_bounds__(kBlock) ca_world_kernel(const __grid_constant_
   int32_t* sidx_row = (p.sidx && world_ok) ? p.sidx + g * p.M : nullptr;
 
   Agent a;
-  if (valid) load_agent(blk, lane, a); else zero_agent(a);
+  if (valid) load_agent<!kStep>(blk, lane, a); else zero_agent(a);  // a step overwrites the velocity before using it
 
   bool do_reset;  // world reloads its injected initial state
-  if (kStep) {
-    // ---- _take_action (:217-252): every agent picks its command first ...
-    const bool was_done = (a.flags & CA_F_DONE_MASK) != 0;
-    float cmd_speed = 0.f, cmd_dh = 0.f;  // all_actions is float32 (:238)
-    if (valid && !was_done) {
-      if (a.policy == CA_POLICY_NONCOOP) {
-        // NonCooperativePolicy.find_next_action (policies/NonCooperativePolicy.py:9-22) reads the ego
-        // heading of the pre-step state
-        Ego e0;
-        ego_axes(a.px, a.py, a.gx, a.gy, e0);
-        cmd_speed = (float)a.ps;
-        cmd_dh = (float)(-heading_ego_exact(e0, a.hd));
-      } else if (a.policy == CA_POLICY_LEARNING_GA3C) {  // LearningPolicyGA3C.external_action_to_action
-        int k = p.actions[g];
-        k = k < 0 ? 0 : (k > 10 ? 10 : k);
-        cmd_speed = (float)(a.ps * kActSpeed[k]);
-        cmd_dh = (float)kActDhead[k];
-      } else if (a.policy == CA_POLICY_LEARNING) {  // LearningPolicy.external_action_to_action
-        double e0 = 0.0, e1 = 0.5;
-        if (p.cont) { e0 = p.cont[2 * g]; e1 = p.cont[2 * g + 1]; }
-        cmd_speed = (float)(a.ps * e0);
-        cmd_dh = (float)(p.max_heading_change * (2. * e1 - 1.));
-      } else if (a.policy == CA_POLICY_STATIC) {  // StaticPolicy: goal := pos
-        a.gx = a.px;
-        a.gy = a.py;
-      }
-    }
-    // ---- ... then all agents move (Agent.take_action, agent.py:190-238)
-    if (valid) {
-      if (was_done) {
-        if (a.flags & CA_F_AT_GOAL) a.flags |= CA_F_WAS_AT_GOAL;
-        if (a.flags & CA_F_IN_COLLISION) a.flags |= CA_F_WAS_IN_COLLISION;
-        a.vx = 0.0;
-        a.vy = 0.0;
-      } else {
-        // UnicycleDynamics.step (dynamics/UnicycleDynamics.py:14-47)
-        const double speed = (double)cmd_speed;
-        const double h = wrap_angle((double)cmd_dh + a.hd);
-        double sh, ch;
-        sincos(h, &sh, &ch);
-        a.px += speed * ch * p.dt;
-        a.py += speed * sh * p.dt;
-        a.vx = speed * ch;
-        a.vy = speed * sh;
-        a.hd = h;
-        const double ex = a.px - a.gx, ey = a.py - a.gy;  // _check_if_at_goal (agent.py:148-151)
-        if (ex * ex + ey * ey <= p.thr_sq) a.flags |= CA_F_AT_GOAL; else a.flags &= ~CA_F_AT_GOAL;
-        a.tr -= p.dt;  // agent.py:232-236
-        if (a.tr <= 0.0) a.flags |= CA_F_RAN_OUT_OF_TIME;
-      }
-    }
-  }
+  if (kStep) step_take_action(p, a, (valid && a.policy == CA_POLICY_LEARNING_GA3C) ? p.actions[g] : 0, g, valid);
 
   Ego e = ego_frame(a.px, a.py, a.gx, a.gy, a.hd);
 
@@ -494,35 +551,10 @@ __global__ void __launch_bounds__(kBlock) ca_world_kernel(const __grid_constant_
     bool coll;
     double nearest;
     pair_pass<true>(p, sm, a, e, valid, n, i, base, tid, coll, nearest);
-    // ---- _compute_rewards (:319-368)
-    double r = p.r_step;
-    if (valid) {
-      if (a.flags & CA_F_AT_GOAL) {
-        if (!(a.flags & CA_F_WAS_AT_GOAL)) r = p.r_goal;
-      } else if (!(a.flags & CA_F_WAS_IN_COLLISION)) {
-        if (coll) {
-          r = p.r_coll;
-          a.flags |= CA_F_IN_COLLISION;
-        } else if (nearest <= p.close_range) {
-          r = -0.1 - nearest / 2.;
-        }
-      }
-      r = fmin(fmax(r, p.r_min), p.r_max);
-      if (p.over_mode == CA_OVER_FIRST_AGENT_DONE && i > 0) r = 0.0;  // rewards = rewards[0] (:365-366)
-    } else {
-      r = 0.0;
-    }
-    // ---- _check_which_agents_done (:411-439)
-    const bool dn = valid ? (a.flags & CA_F_DONE_MASK) != 0 : true;
-    const bool learning = valid && (a.policy == CA_POLICY_LEARNING_GA3C || a.policy == CA_POLICY_LEARNING);
-    bool blocks_over;  // this agent keeps the episode alive
-    if (p.over_mode == CA_OVER_ALL_DONE) blocks_over = valid && !dn;
-    else if (p.over_mode == CA_OVER_FIRST_AGENT_DONE) blocks_over = valid && i == 0 && !dn;
-    else blocks_over = learning && !dn;
-    const unsigned alive = __ballot_sync(kFull, blocks_over) & gmask;
-    const bool over = alive == 0u;
+    bool dn, over;
+    const float r = step_reward_done(p, a, valid, i, coll, nearest, gmask, dn, over);
     if (world_ok) {
-      p.reward[g] = (float)r;
+      p.reward[g] = r;
       p.done[g] = dn ? 1 : 0;
       if (i == 0) p.over[w] = over ? 1 : 0;
     }
@@ -540,7 +572,7 @@ __global__ void __launch_bounds__(kBlock) ca_world_kernel(const __grid_constant_
       n = blk_nag(blk0)[wl];
       valid = i < n;
       if (i == 0) { blk_nag(blk)[wl] = n; p.consumed[w] = 1; }
-      if (valid) load_agent(blk0, lane, a); else zero_agent(a);
+      if (valid) load_agent<false>(blk0, lane, a); else zero_agent(a);  // a snapshot is at rest
       e = ego_frame(a.px, a.py, a.gx, a.gy, a.hd);
     }
     bool c_unused;

@@ -237,7 +237,7 @@ __global__ void __launch_bounds__(kGenWarps * 32) generate_scenarios_kernel(cons
     blk[O_PX + dst] = live ? ag.px[i] : 0.0; blk[O_PY + dst] = live ? ag.py[i] : 0.0;
     blk[O_GX + dst] = live ? ag.gx[i] : 0.0; blk[O_GY + dst] = live ? ag.gy[i] : 0.0;
     blk[O_HD + dst] = live ? heading : 0.0;
-    blk[O_VX + dst] = 0.0; blk[O_VY + dst] = 0.0; blk[O_TR + dst] = t0;
+    blk_spd(blk)[dst] = 0.f; blk[O_TR + dst] = t0;
     blk[O_RAD + dst] = live ? ag.rd[i] : 0.0; blk[O_PS + dst] = live ? ag.sp[i] : 0.0;
     blk_flags(blk)[dst] = 0; blk_policy(blk)[dst] = live ? (uint8_t)pol : 0;
   }

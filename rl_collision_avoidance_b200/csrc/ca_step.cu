@@ -9,8 +9,8 @@
 #include <string>
 
 #include "ca_kernels.cuh"
-#include "ca_step_pipe.cuh"
 #include "ca_step_fast.cuh"
+#include "ca_step_stream.cuh"
 #include "ca_ga3c.cuh"
 #include "ca_scenarios.cuh"
 
@@ -63,7 +63,9 @@ struct ca_env {
   int tile_floats = 0;
   bool bulk_ok = true;
   bool force_generic = false;
-  int kernel_choice = 1;       // 1 = one-shot specialised kernel (default, fastest measured), 0 = pipelined persistent kernel
+  int kernel_choice = 1;       // 1 = one-shot specialised kernel, 0 = streaming persistent kernel (ca_step_stream.cuh)
+  bool dynamic_sched = true;   // streaming kernel: chunks pulled from the ticket counter (CA_STREAM_STATIC=1: strided)
+  unsigned* ticket = nullptr;  // streaming kernel: self-resetting work counter
   bool store_vec4 = false;     // CA_STORE_MODE=vec4: 128-bit copy-out instead of the TMA bulk store (one-shot kernel)
   bool use_pdl = true;         // programmatic dependent launch for step kernels (CA_DISABLE_PDL=1 turns it off)
   int pipe_min_blocks = 0;     // 0 = default instantiation
@@ -125,7 +127,7 @@ __global__ void unpack_init_kernel(const double* __restrict__ init, const int32_
     if (!(t0 > dt)) t0 = dt;
   }
   ca::Agent a;
-  a.px = v[CA_I_PX]; a.py = v[CA_I_PY]; a.hd = v[CA_I_HEADING]; a.vx = 0.0; a.vy = 0.0; a.tr = i < n ? t0 : 0.0;
+  a.px = v[CA_I_PX]; a.py = v[CA_I_PY]; a.hd = v[CA_I_HEADING]; a.vx = 0.0; a.vy = 0.0; a.spd = 0.f; a.tr = i < n ? t0 : 0.0;
   a.gx = v[CA_I_GX]; a.gy = v[CA_I_GY]; a.rad = v[CA_I_RADIUS]; a.ps = v[CA_I_PREF_SPEED];
   a.flags = 0; a.policy = (int)v[CA_I_POLICY];
   ca::store_agent(b0, lane, a, true, true);
@@ -167,6 +169,7 @@ ca::Params make_params(const ca_env* e) {
   p.max_heading_change = c.max_heading_change;
   p.sensing_horizon = c.sensing_horizon;
   p.s = e->s; p.s0 = e->s0; p.consumed = e->consumed;
+  p.ticket = e->ticket; p.dynamic_sched = e->dynamic_sched ? 1 : 0;
   return p;
 }
 
@@ -188,23 +191,23 @@ bool has_fast_kernel(const ca_env* e) {
 
 cudaError_t set_fast_smem_attr(int A, int bytes);
 
-// Instantiations of the pipelined kernel: (agent slots, min CTAs per SM used for register allocation).
-#define CA_PIPE_VARIANTS(X) X(2, 6) X(3, 6) X(4, 5) X(4, 6) X(4, 7) X(5, 5) X(6, 5) X(8, 4) X(10, 3)
+// Instantiations of the streaming kernel: (agent slots, min CTAs per SM used for register allocation).
+#define CA_PIPE_VARIANTS(X) X(2, 8) X(3, 8) X(4, 6) X(4, 7) X(4, 8) X(5, 6) X(6, 6) X(8, 5) X(8, 6) X(10, 4) X(10, 5)
 
 int default_pipe_min_blocks(int A) {
   switch (A) {
-    case 2: case 3: return 6;
-    case 4: return 5;
-    case 5: case 6: return 5;
-    case 8: return 4;
-    default: return 3;
+    case 2: case 3: return 8;
+    case 4: return 7;
+    case 5: case 6: return 6;
+    case 8: return 6;
+    default: return 5;
   }
 }
 
 const void* pipe_kernel_ptr(int A, int mb, bool dbg = false) {
 #define X(a, b)          \
   if (A == a && mb == b) \
-    return dbg ? (const void*)ca::ca_step_pipe_kernel<a, b, true> : (const void*)ca::ca_step_pipe_kernel<a, b, false>;
+    return dbg ? (const void*)ca::ca_step_stream_kernel<a, b, true> : (const void*)ca::ca_step_stream_kernel<a, b, false>;
   CA_PIPE_VARIANTS(X)
 #undef X
   return nullptr;
@@ -273,9 +276,9 @@ int launch_world_kernel(ca_env* e, bool step, ca::Params& p, cudaStream_t st) {
   p.warp_store = ((e->tile_floats / kWarps) % 4) == 0 ? 1 : 0;
   int rc;
   // the instantiations with neighbour-index output / finite sensing horizon are only used when asked for
-  const bool dbg = p.sidx != nullptr || std::isfinite(e->cfg.sensing_horizon);
+  const bool dbg = p.sidx != nullptr || std::isfinite(e->cfg.sensing_horizon) || e->M != e->A - 1;
   if (step && has_fast_kernel(e) && e->kernel_choice == 0) {
-    p.use_bulk_store = (e->bulk_ok && aligned16(p.obs)) ? 1 : 0;  // per-warp tile; its own size check is in-kernel
+    p.use_bulk_store = e->bulk_ok ? 1 : 0;  // the kernel aligns the tile to the destination's 16-byte phase itself
     rc = launch_pdl(pipe_kernel_ptr(e->A, e->pipe_min_blocks, dbg), e->pipe_grid, e->smem_pipe, st, p, e->use_pdl);
   } else if (step && has_fast_kernel(e)) {
     if (e->store_vec4 && aligned16(p.obs) && p.warp_store) p.use_bulk_store = 2;
@@ -416,7 +419,9 @@ int ca_create(const ca_config* cfg, ca_env** out) {
   }
   const char* kc = getenv("CA_STEP_KERNEL");  // "oneshot" (default) | "pipe" | "generic"
   if (kc && strcmp(kc, "oneshot") == 0) e->kernel_choice = 1;
-  if (kc && strcmp(kc, "pipe") == 0) e->kernel_choice = 0;
+  if (kc && (strcmp(kc, "stream") == 0 || strcmp(kc, "pipe") == 0)) e->kernel_choice = 0;
+  const char* ss = getenv("CA_STREAM_STATIC");
+  e->dynamic_sched = !(ss && ss[0] == '1');
   const char* sm = getenv("CA_STORE_MODE");
   e->store_vec4 = sm && strcmp(sm, "vec4") == 0;
   const char* np = getenv("CA_DISABLE_PDL");
@@ -427,8 +432,7 @@ int ca_create(const ca_config* cfg, ca_env** out) {
     const char* mb = getenv("CA_PIPE_MINBLOCKS");
     if (mb && pipe_kernel_ptr(e->A, atoi(mb))) e->pipe_min_blocks = atoi(mb);
     const void* fn = pipe_kernel_ptr(e->A, e->pipe_min_blocks);
-    const int warp_tile_bytes = ((e->tile_floats / kWarps) * 4 + 15) / 16 * 16;
-    e->smem_pipe = (size_t)kWarps * (ca::kStageBytes + warp_tile_bytes + 16);
+    e->smem_pipe = (size_t)kWarps * ca::stream_warp_region(e->tile_floats / kWarps);
     ce = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem_pipe);
     if (ce == cudaSuccess)
       ce = cudaFuncSetAttribute(pipe_kernel_ptr(e->A, e->pipe_min_blocks, true), cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -441,6 +445,8 @@ int ca_create(const ca_config* cfg, ca_env** out) {
       if (pg && atoi(pg) > 0 && atoi(pg) < per_sm) per_sm = atoi(pg);
       const int resident = sms * (per_sm > 0 ? per_sm : 1);
       e->pipe_grid = e->grid < resident ? e->grid : resident;
+      const char* sg = getenv("CA_STREAM_GRID");  // tests: a tiny grid makes every warp loop over many chunks
+      if (sg && atoi(sg) > 0 && atoi(sg) < e->pipe_grid) e->pipe_grid = atoi(sg);
     }
   }
   if (ce != cudaSuccess) {
@@ -448,8 +454,9 @@ int ca_create(const ca_config* cfg, ca_env** out) {
     return fail(CA_ERR_CUDA, "kernel image not usable on this device (built for sm_100a): %s", cudaGetErrorString(ce));
   }
   const size_t slab_bytes = (size_t)e->n_chunks * ca::kBlkBytes * 2;
-  if (cudaMalloc(&e->slab, slab_bytes) != cudaSuccess || cudaMalloc(&e->consumed, (size_t)e->W) != cudaSuccess) {
-    cudaFree(e->slab); cudaFree(e->consumed);
+  if (cudaMalloc(&e->slab, slab_bytes) != cudaSuccess || cudaMalloc(&e->consumed, (size_t)e->W) != cudaSuccess ||
+      cudaMalloc(&e->ticket, 128) != cudaSuccess) {
+    cudaFree(e->slab); cudaFree(e->consumed); cudaFree(e->ticket);
     delete e;
     cudaGetLastError();
     return fail(CA_ERR_ALLOC, "cudaMalloc of %zu state bytes failed", slab_bytes);
@@ -457,6 +464,7 @@ int ca_create(const ca_config* cfg, ca_env** out) {
   cudaMemset(e->slab, 0, slab_bytes);
   carve(e);
   cudaMemset(e->consumed, 0, (size_t)e->W);
+  cudaMemset(e->ticket, 0, 128);
   *out = e;
   return CA_OK;
 }
@@ -465,7 +473,7 @@ int ca_destroy(ca_env* e) {
   if (!e) return CA_OK;
   DeviceGuard guard(e->cfg.device);
   cudaDeviceSynchronize();
-  cudaFree(e->slab); cudaFree(e->consumed);
+  cudaFree(e->slab); cudaFree(e->consumed); cudaFree(e->ticket);
   cudaFree(e->d_actions); cudaFree(e->d_cont); cudaFree(e->d_obs); cudaFree(e->d_reward);
   cudaFree(e->d_done); cudaFree(e->d_over); cudaFree(e->d_mask); cudaFree(e->d_sidx);
   if (e->hstream) cudaStreamDestroy(e->hstream);

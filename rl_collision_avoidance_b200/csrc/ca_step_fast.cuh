@@ -1,19 +1,196 @@
-// ca_step_fast.cuh — the one-shot step kernel specialised on the number of agent slots per world (kA): the default.
+// ca_step_fast.cuh — the step kernels specialised on the number of agent slots per world (kA).
 //
-// Same algorithm, data layout and numerics as ca_world_kernel<true> (ca_kernels.cuh), but with kA a
-// compile-time constant every per-other loop is fully unrolled: the lane's int32 sort keys, p_orth and centre
-// distances of its (kA-1) potential neighbours live in registers (shared with ca_step_pipe.cuh: pipe_pair_pass /
-// pipe_write_obs_row), the neighbour order is a pairwise rank (each unordered pair of keys is compared once) and
-// nothing but the finished observation rows goes through shared memory; each warp hands its rows to one TMA bulk
-// store.  One CTA = 4 warps = 4 chunks of floor(32/kA) worlds; the launch-bounds occupancy target (kMinBlocks) is
-// tuned per kA so that the grid finishes in as few rounds of resident warps as possible.  Used for closest_first /
-// closest_last sorting; time_to_impact sorting, reset, and agent counts without an instantiation run on the
-// generic kernel.
+// Same algorithm, data layout and numerics as ca_world_kernel<true> (ca_kernels.cuh; the step body itself —
+// step_take_action / step_reward_done — is literally shared), but with kA a compile-time constant every per-other loop
+// is fully unrolled: the lane's int32 sort keys, p_orth and centre distances of its (kA-1) potential neighbours live
+// in registers (fast_pair_pass / fast_write_obs_row), the neighbour order is a pairwise rank (each unordered pair of
+// keys is compared once) and nothing but the finished observation rows goes through shared memory.
+//   ca_step_kernel         one-shot: one CTA = 4 warps = 4 chunks of floor(32/kA) worlds, one TMA bulk store per warp
+//   ca_step_stream_kernel  (ca_step_stream.cuh) persistent: warps pull chunks from an atomic counter, the next chunk's
+//                          state block is in flight (TMA bulk load + mbarrier) while the current one is computed
+// Used for closest_first / closest_last sorting; time_to_impact sorting, reset, and agent counts without an
+// instantiation run on the generic kernel.
 #pragma once
+#include <limits.h>
+
 #include "ca_kernels.cuh"
-#include "ca_step_pipe.cuh"
 
 namespace ca {
+
+template <int kA>
+struct OthersLite {
+  static constexpr int kN = kA > 1 ? kA - 1 : 1;
+  int key[kN];      // rint(100 * dist_2_other); INT_MAX for an absent / unobserved other
+  double po[kN];    // p_orth (float64: it breaks ties between equal keys)
+  // observation-only float32 values, final already: p_parallel and the boundary distance (the other's radius and
+  // velocity are fetched by float32 shuffles when the row is written)
+  float pprl[kN], d2o[kN];
+};
+
+// Number of per-other iterations the lanes of this warp need: kA - 1, or for the larger specialisations (ragged
+// batches: BASELINE configs[3]) the largest agent count among the warp's worlds minus one — warp-uniform, so the
+// unrolled loops below skip whole iterations without divergence.
+template <int kA>
+__device__ __forceinline__ int others_bound(int n) {
+  if (kA < 6) return kA - 1;
+  return __reduce_max_sync(kFull, n) - 1;
+}
+
+// kGen selects the general variant (finite SENSING_HORIZON, neighbour-index output for parity tests, M < kA - 1
+// clipping); the production instantiation (kGen = false) carries neither their instructions nor their registers.
+// First loop of the sensor (OtherAgentsStatesSensor.sense :72-103) fused with _check_for_collisions (:370-409).
+template <int kA, bool kCollide, bool kGen>
+__device__ __forceinline__ void fast_pair_pass(const Params& p, const Agent& a, const Ego& e, bool valid, int n, int nm1,
+                                               int i, int base, OthersLite<kA>& o, bool& coll, double& nearest) {
+  coll = false;
+  nearest = INFINITY;
+  const bool horizon = kGen && isfinite(p.sensing_horizon);
+#pragma unroll
+  for (int k = 0; k < kA - 1; ++k) {
+    o.key[k] = INT_MAX;
+    o.po[k] = 0.0;
+    o.pprl[k] = 0.f; o.d2o[k] = 0.f;
+    if (kA >= 6 && k >= nm1) continue;   // warp-uniform
+    const int j = k + (k >= i ? 1 : 0);
+    const int src = (base + j) & 31;
+    const double xj = shfl_d(a.px, src), yj = shfl_d(a.py, src), rj = shfl_d(a.rad, src);
+    const bool live = valid && j < n;
+    const double rx = xj - a.px, ry = yj - a.py;
+    const double d = sqrt(rx * rx + ry * ry);  // l2norm (util.py:8-12)
+    if (kCollide && live) {
+      const double R = a.rad + rj;
+      if (d <= R) coll = true;
+      if (j > i) nearest = fmin(nearest, d - R);  // only the lower index is updated (:393)
+    }
+    const bool seen = live && !(horizon && d > p.sensing_horizon);
+    const double d2o = d - a.rad - rj;
+    if (seen) o.key[k] = __double2int_rn(d2o * 100.0);
+    o.po[k] = dot2(rx, ry, -e.pry, e.prx);
+    o.pprl[k] = obs_pprl(rx, ry, e);
+    o.d2o[k] = (float)d2o;
+  }
+}
+
+__device__ __forceinline__ bool key_first(int q1, double p1, int q2, double p2) {
+  return (q1 < q2) || (q1 == q2 && p1 <= p2);
+}
+
+// slot[k] = number of keys among the first kUse that sort before key k (stable: equal keys keep index order); each
+// unordered pair is compared once
+template <int kN, int kUse>
+__device__ __forceinline__ void rank_pairs(const int* key, const double* po, int* slot) {
+#pragma unroll
+  for (int k1 = 0; k1 < kUse; ++k1)
+#pragma unroll
+    for (int k2 = k1 + 1; k2 < kUse; ++k2) {
+      const bool b = key_first(key[k1], po[k1], key[k2], po[k2]);
+      slot[k1] += b ? 0 : 1;
+      slot[k2] += b ? 1 : 0;
+    }
+}
+// the same with the (warp-uniform) number of keys in use known only at run time: one fully unrolled body per count
+template <int kN, int kUse>
+__device__ __forceinline__ void rank_dispatch(int nm1, const int* key, const double* po, int* slot) {
+  if constexpr (kUse >= 2) {
+    if (nm1 >= kUse) rank_pairs<kN, kUse>(key, po, slot);
+    else rank_dispatch<kN, kUse - 1>(nm1, key, po, slot);
+  }
+}
+
+// All lanes of the warp clear `nfloats` floats at t (the widest store the alignment of t and nfloats allows).
+__device__ __forceinline__ void zero_warp_tile(float* t, int nfloats, int lane) {
+  const uintptr_t addr = reinterpret_cast<uintptr_t>(t);
+  if (((addr | (uintptr_t)(nfloats * 4)) & 15u) == 0) {
+    float4* t4 = reinterpret_cast<float4*>(t);
+    for (int q = lane; q < nfloats / 4; q += 32) t4[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+  } else if (((addr | (uintptr_t)(nfloats * 4)) & 7u) == 0) {
+    float2* t2 = reinterpret_cast<float2*>(t);
+    for (int q = lane; q < nfloats / 2; q += 32) t2[q] = make_float2(0.f, 0.f);
+  } else {
+    for (int q = lane; q < nfloats; q += 32) t[q] = 0.f;
+  }
+}
+
+// Second loop of the sensor (:105-144) + the dense row of GCA/envs/wrappers.py:130-139: rank the others, (general
+// variant: clip to M, closest_last order), write the lane's observation row into the tile.
+template <int kA, bool kGen>
+__device__ __forceinline__ void fast_write_obs_row(const Params& p, const Agent& a, const Ego& e, bool world_ok,
+                                                   bool valid, int nm1, int i, int base, const OthersLite<kA>& o,
+                                                   float* row, int32_t* sidx_row_in, float* wt, int wt_floats) {
+  int32_t* const sidx_row = kGen ? sidx_row_in : nullptr;
+  constexpr int kN = kA - 1;
+  constexpr int kNN = kN > 0 ? kN : 1;
+  const int M = kGen ? p.M : kN;
+  int count = 0;
+  int key[kNN];
+#pragma unroll
+  for (int k = 0; k < kN; ++k) {
+    key[k] = o.key[k];
+    count += (key[k] != INT_MAX) ? 1 : 0;
+  }
+  if (kGen && count > M) {   // first sort + clip to the M closest
+    int rank1[kNN];
+#pragma unroll
+    for (int k = 0; k < kN; ++k) rank1[k] = 0;
+    rank_pairs<kNN, kN>(o.key, o.po, rank1);
+#pragma unroll
+    for (int k = 0; k < kN; ++k)
+      if (rank1[k] >= M) key[k] = INT_MAX;
+    count = M;
+  }
+  if (p.sort_method == CA_SORT_CLOSEST_LAST) {
+#pragma unroll
+    for (int k = 0; k < kN; ++k)
+      if (key[k] != INT_MAX) key[k] = -key[k];
+  }
+  int slot[kNN];
+#pragma unroll
+  for (int k = 0; k < kN; ++k) slot[k] = 0;
+  if (kA >= 6) rank_dispatch<kNN, kN>(nm1, key, o.po, slot);
+  else rank_pairs<kNN, kN>(key, o.po, slot);
+  // Rows of absent agents and the unused tail of short rows are zeros (wrappers.py:115-139).  A lane clearing its own
+  // row serialises against the lanes that have values to write, so when any row of the warp needs zeros all 32 lanes
+  // clear the warp's whole tile first with wide stores (ragged batches: ~20 instructions instead of ~300).
+  const bool need_zeros = world_ok && (!valid || count < M);
+  if (__any_sync(kFull, need_zeros)) {
+    zero_warp_tile(wt, wt_floats, threadIdx.x & 31);
+    __syncwarp();
+  }
+  if (world_ok) {
+    if (valid) {
+      row[0] = (a.policy == CA_POLICY_LEARNING_GA3C || a.policy == CA_POLICY_LEARNING) ? 1.f : 0.f;
+      row[1] = (float)count;
+      row[2] = (float)e.dist;
+      row[3] = e.hego;
+      row[4] = (float)a.ps;
+      row[5] = (float)a.rad;
+      if (sidx_row) for (int k = count; k < M; ++k) sidx_row[k] = -1;
+    } else {
+      if (sidx_row) for (int k = 0; k < M; ++k) sidx_row[k] = -1;
+    }
+  }
+  // second loop of the sensor: the others' radius and velocity still have to be fetched, as float32
+  const float prxf = (float)e.prx, pryf = (float)e.pry, raf = (float)a.rad;
+  const float vxf = (float)a.vx, vyf = (float)a.vy;
+#pragma unroll
+  for (int k = 0; k < kN; ++k) {
+    if (kA >= 6 && k >= nm1) continue;   // warp-uniform
+    const int j = k + (k >= i ? 1 : 0);
+    const int src = (base + j) & 31;
+    const float vxj = __shfl_sync(kFull, vxf, src), vyj = __shfl_sync(kFull, vyf, src);
+    const float rrj = __shfl_sync(kFull, raf, src);
+    if (valid && key[k] != INT_MAX) {
+      float* s = row + CA_OBS_HOST_LEN + CA_OBS_OTHER_LEN * slot[k];
+      s[0] = o.pprl[k];
+      s[1] = (float)o.po[k];
+      obs_vel(vxj, vyj, prxf, pryf, s[2], s[3]);
+      s[4] = rrj;
+      s[5] = raf + rrj;
+      s[6] = o.d2o[k];
+      if (sidx_row) sidx_row[slot[k]] = j;
+    }
+  }
+}
 
 // Warp-level store of the warp's observation rows (its wpw worlds are contiguous in global memory).
 template <int kA>
@@ -47,7 +224,7 @@ __device__ __forceinline__ void fast_store_warp_tile(const Params& p, const floa
   for (int q = lane; q < nfloats; q += 32) dst[q] = wtile[q];
 }
 
-template <int kA, int kMinBlocks, bool kDbg>
+template <int kA, int kMinBlocks, bool kGen>
 __global__ void __launch_bounds__(kBlock, kMinBlocks) ca_step_kernel(const __grid_constant__ Params p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   constexpr int wpw = (32 / kA) < 16 ? (32 / kA) : 16;
@@ -83,58 +260,14 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks) ca_step_kernel(const __gri
   }
   if (!valid) { zero_agent(a); act = 0; }
 
-  // ---- _take_action (:217-252)
-  const bool was_done = (a.flags & CA_F_DONE_MASK) != 0;
-  float cmd_speed = 0.f, cmd_dh = 0.f;
-  if (valid && !was_done) {
-    if (a.policy == CA_POLICY_NONCOOP) {
-      Ego e0;
-      ego_axes(a.px, a.py, a.gx, a.gy, e0);
-      cmd_speed = (float)a.ps;
-      cmd_dh = (float)(-heading_ego_exact(e0, a.hd));
-    } else if (a.policy == CA_POLICY_LEARNING_GA3C) {
-      const int k = act < 0 ? 0 : (act > 10 ? 10 : act);
-      cmd_speed = (float)(a.ps * kActSpeed[k]);
-      cmd_dh = (float)kActDhead[k];
-    } else if (a.policy == CA_POLICY_LEARNING) {
-      double e0 = 0.0, e1 = 0.5;
-      if (p.cont) { e0 = p.cont[2 * g]; e1 = p.cont[2 * g + 1]; }
-      cmd_speed = (float)(a.ps * e0);
-      cmd_dh = (float)(p.max_heading_change * (2. * e1 - 1.));
-    } else if (a.policy == CA_POLICY_STATIC) {
-      a.gx = a.px;
-      a.gy = a.py;
-    }
-  }
-  // ---- Agent.take_action (agent.py:190-238)
-  if (valid) {
-    if (was_done) {
-      if (a.flags & CA_F_AT_GOAL) a.flags |= CA_F_WAS_AT_GOAL;
-      if (a.flags & CA_F_IN_COLLISION) a.flags |= CA_F_WAS_IN_COLLISION;
-      a.vx = 0.0;
-      a.vy = 0.0;
-    } else {
-      const double speed = (double)cmd_speed;
-      const double h = wrap_angle((double)cmd_dh + a.hd);
-      double sh, ch;
-      sincos(h, &sh, &ch);
-      a.px += speed * ch * p.dt;
-      a.py += speed * sh * p.dt;
-      a.vx = speed * ch;
-      a.vy = speed * sh;
-      a.hd = h;
-      const double ex = a.px - a.gx, ey = a.py - a.gy;
-      if (ex * ex + ey * ey <= p.thr_sq) a.flags |= CA_F_AT_GOAL; else a.flags &= ~CA_F_AT_GOAL;
-      a.tr -= p.dt;
-      if (a.tr <= 0.0) a.flags |= CA_F_RAN_OUT_OF_TIME;
-    }
-  }
+  step_take_action(p, a, act, g, valid);
 
   Ego e = ego_frame(a.px, a.py, a.gx, a.gy, a.hd);
   OthersLite<kA> o;
   bool coll;
   double nearest;
-  pipe_pair_pass<kA, true, kDbg>(p, a, e, valid, n, i, base, o, coll, nearest);
+  const int nm1 = others_bound<kA>(n);
+  fast_pair_pass<kA, true, kGen>(p, a, e, valid, n, nm1, i, base, o, coll, nearest);
 
   if (p.prefetch_chunks > 0 && lane == 0) {
     // The grid runs in about two rounds of resident CTAs.  By now this round's own load burst has drained and DRAM is
@@ -147,35 +280,10 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks) ca_step_kernel(const __gri
     }
   }
 
-  // ---- _compute_rewards (:319-368)
-  double r = p.r_step;
-  if (valid) {
-    if (a.flags & CA_F_AT_GOAL) {
-      if (!(a.flags & CA_F_WAS_AT_GOAL)) r = p.r_goal;
-    } else if (!(a.flags & CA_F_WAS_IN_COLLISION)) {
-      if (coll) {
-        r = p.r_coll;
-        a.flags |= CA_F_IN_COLLISION;
-      } else if (nearest <= p.close_range) {
-        r = -0.1 - nearest / 2.;
-      }
-    }
-    r = fmin(fmax(r, p.r_min), p.r_max);
-    if (p.over_mode == CA_OVER_FIRST_AGENT_DONE && i > 0) r = 0.0;
-  } else {
-    r = 0.0;
-  }
-  // ---- _check_which_agents_done (:411-439)
-  const bool dn = valid ? (a.flags & CA_F_DONE_MASK) != 0 : true;
-  const bool learning = valid && (a.policy == CA_POLICY_LEARNING_GA3C || a.policy == CA_POLICY_LEARNING);
-  bool blocks_over;
-  if (p.over_mode == CA_OVER_ALL_DONE) blocks_over = valid && !dn;
-  else if (p.over_mode == CA_OVER_FIRST_AGENT_DONE) blocks_over = valid && i == 0 && !dn;
-  else blocks_over = learning && !dn;
-  const unsigned alive = __ballot_sync(kFull, blocks_over) & gmask;
-  const bool over = alive == 0u;
+  bool dn, over;
+  const float r = step_reward_done(p, a, valid, i, coll, nearest, gmask, dn, over);
   if (world_ok) {
-    p.reward[g] = (float)r;
+    p.reward[g] = r;
     p.done[g] = dn ? 1 : 0;
     if (i == 0) p.over[w] = over ? 1 : 0;
   }
@@ -185,7 +293,7 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks) ca_step_kernel(const __gri
   // here instead of occupying registers through the ranking / row code.
   if (!__any_sync(kFull, do_reset)) {
     if (valid) store_agent(blk, lane, a, a.policy == CA_POLICY_STATIC, false);
-    pipe_write_obs_row<kA, kDbg>(p, a, e, world_ok, valid, i, base, o, row, sidx_row);
+    fast_write_obs_row<kA, kGen>(p, a, e, world_ok, valid, nm1, i, base, o, row, sidx_row, wtile, wpw * kA * p.L);
   } else {
     // DummyVecEnv semantics: worlds that finished reload their injected initial state and observe again;
     // the other worlds of the warp observe their post-step state.
@@ -194,15 +302,16 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks) ca_step_kernel(const __gri
       n = blk_nag(blk0)[wl];
       valid = i < n;
       if (i == 0) { blk_nag(blk)[wl] = n; p.consumed[w] = 1; }
-      if (valid) load_agent(blk0, lane, a); else zero_agent(a);
+      if (valid) load_agent<false>(blk0, lane, a); else zero_agent(a);  // a snapshot is at rest
       e = ego_frame(a.px, a.py, a.gx, a.gy, a.hd);
     }
     if (valid || do_reset)  // a reset rewrites every slot of the world (the new scenario may have fewer agents)
       store_agent(blk, lane, a, a.policy == CA_POLICY_STATIC, do_reset);
     bool c_unused;
     double n_unused;
-    pipe_pair_pass<kA, false, kDbg>(p, a, e, valid, n, i, base, o, c_unused, n_unused);
-    pipe_write_obs_row<kA, kDbg>(p, a, e, world_ok, valid, i, base, o, row, sidx_row);
+    const int nm1r = others_bound<kA>(n);
+    fast_pair_pass<kA, false, kGen>(p, a, e, valid, n, nm1r, i, base, o, c_unused, n_unused);
+    fast_write_obs_row<kA, kGen>(p, a, e, world_ok, valid, nm1r, i, base, o, row, sidx_row, wtile, wpw * kA * p.L);
   }
 
   if (p.warp_store) fast_store_warp_tile<kA>(p, wtile, first_world_warp, lane);

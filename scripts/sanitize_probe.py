@@ -16,7 +16,7 @@ from rl_collision_avoidance_b200.scenarios import random_worlds
 
 rng = np.random.default_rng(0)
 PART = sys.argv[1] if len(sys.argv) > 1 else "all"
-for kern in (("oneshot", "pipe", "generic") if PART in ("all", "step") else ()):
+for kern in (("oneshot", "stream", "generic") if PART in ("all", "step") else ()):
     os.environ["CA_STEP_KERNEL"] = kern
     for A, W in ((4, 531), (10, 77), (3, 100)):
         init, nag = random_worlds(W, A, rng, num_agents=rng.integers(2, A + 1, W), policies=['noncoop', 'learning_ga3c', 'static'],

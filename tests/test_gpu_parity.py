@@ -295,17 +295,21 @@ def test_bulk_store_and_plain_store_paths_agree(monkeypatch):
                                       (5, 2, "closest_last"), (6, 5, "closest_first"), (8, 3, "closest_first"),
                                       (10, 9, "closest_last")])
 def test_specialised_and_generic_kernels_agree_bitwise(monkeypatch, A, M, sort):
-    """ca_step_kernel<A> (one-shot, unrolled, register keys), ca_step_pipe_kernel<A> (persistent, TMA-prefetched state,
-    int keys) and the generic ca_world_kernel<true> are the same arithmetic; PDL launches change nothing."""
+    """ca_step_kernel<A> (one-shot, unrolled, register keys), ca_step_stream_kernel<A> (persistent, chunks pulled from the
+    ticket counter or strided, TMA-prefetched state; a 3-CTA grid makes every warp loop over many chunks) and the generic
+    ca_world_kernel<true> are the same arithmetic; PDL launches change nothing."""
     rng = np.random.default_rng(90 + A)
     W = 777
     init, nag = _random_worlds(rng, W, A, 3.0 + 0.3 * A, policies=(0, 0, 0, 1, 2))
     init2, nag2 = _random_worlds(rng, W, A, 3.0 + 0.3 * A, policies=(0, 0, 0, 1, 2))
     acts = rng.choice([0, 1, 2, 2, 2, 3, 4, 6, 9], size=(40, W, A)).astype(np.int32)
     outs = []
-    for kern, pdl_off in (("generic", "1"), ("oneshot", "0"), ("pipe", "0"), ("oneshot", "1")):
+    for kern, pdl_off, static, grid in (("generic", "1", "0", "0"), ("oneshot", "0", "0", "0"), ("stream", "0", "0", "0"),
+                                        ("oneshot", "1", "0", "0"), ("stream", "0", "0", "3"), ("stream", "1", "1", "2")):
         monkeypatch.setenv("CA_STEP_KERNEL", kern)
         monkeypatch.setenv("CA_DISABLE_PDL", pdl_off)
+        monkeypatch.setenv("CA_STREAM_STATIC", static)
+        monkeypatch.setenv("CA_STREAM_GRID", grid)
         env = _host_env(_abi.default_config(W, A, M, sort_method=_abi.SORT_METHODS[sort], auto_reset=1))
         env.set_world_state(init, nag)
         env.reset()
