@@ -74,11 +74,11 @@ struct Params {
   int sort_method, over_mode, auto_reset;
   int tile_floats;      // floats in the CTA's obs tile = kWarps * wpw * A * L
   int use_bulk_store;   // 1: TMA bulk store of full tiles
-  int warp_store;       // specialised kernel: each warp stores its own rows (warp tile is a multiple of 16 B)
   int prefetch_chunks;  // one-shot kernel: L2-prefetch the state block of chunk + prefetch_chunks (0 = off)
   int dynamic_sched;    // streaming kernel: 1 = warps pull chunks from *ticket, 0 = strided static schedule
   unsigned* ticket;     // streaming kernel: self-resetting work counter (one per env handle)
   double dt, thr_sq, close_range, r_goal, r_coll, r_step, r_min, r_max, max_heading_change, sensing_horizon;
+  float r_goal_f, r_coll_f, r_step_f, r_min_f, r_max_f;  // the reward constants as the float32 that leaves the kernel
   StateBlocks s;        // live state (agent counts inside the blocks)
   StateBlocks s0;       // snapshot injected by ca_set_world_state / ca_set_reset_state / the generator (for reset)
   uint8_t* consumed;    // [W] set to 1 when a world takes its snapshot (the scenario generator refills those)
@@ -276,23 +276,26 @@ __device__ __forceinline__ void zero_agent(Agent& a) {
 // StaticPolicy.py:9-23), then all agents move (Agent.take_action agent.py:190-238, UnicycleDynamics.step
 // dynamics/UnicycleDynamics.py:14-47, _check_if_at_goal agent.py:148-151, time budget agent.py:232-236).
 // `act` is the lane's discrete action, `g` its flat (world, agent) index (continuous actions are read from p.cont).
+// kGen = false (the production instantiations of the specialised kernels): no continuous-action array, game_over =
+// all learning agents done — the launcher picks the general instantiation for anything else.
+template <bool kGen = true>
 __device__ __forceinline__ void step_take_action(const Params& p, Agent& a, int act, size_t g, bool valid) {
   const bool was_done = (a.flags & CA_F_DONE_MASK) != 0;
   float cmd_speed = 0.f, cmd_dh = 0.f;  // all_actions is float32 (:238)
   if (valid && !was_done) {
-    if (a.policy == CA_POLICY_NONCOOP) {
+    if (a.policy == CA_POLICY_LEARNING_GA3C) {
+      const int k = act < 0 ? 0 : (act > 10 ? 10 : act);
+      cmd_speed = (float)(a.ps * kActSpeed[k]);
+      cmd_dh = (float)kActDhead[k];
+    } else if (a.policy == CA_POLICY_NONCOOP) {
       // reads the ego heading of the pre-step state; it feeds the dynamics, so float64 atan2
       Ego e0;
       ego_axes(a.px, a.py, a.gx, a.gy, e0);
       cmd_speed = (float)a.ps;
       cmd_dh = (float)(-heading_ego_exact(e0, a.hd));
-    } else if (a.policy == CA_POLICY_LEARNING_GA3C) {
-      const int k = act < 0 ? 0 : (act > 10 ? 10 : act);
-      cmd_speed = (float)(a.ps * kActSpeed[k]);
-      cmd_dh = (float)kActDhead[k];
     } else if (a.policy == CA_POLICY_LEARNING) {
       double e0 = 0.0, e1 = 0.5;
-      if (p.cont) { e0 = p.cont[2 * g]; e1 = p.cont[2 * g + 1]; }
+      if (kGen && p.cont) { e0 = p.cont[2 * g]; e1 = p.cont[2 * g + 1]; }
       cmd_speed = (float)(a.ps * e0);
       cmd_dh = (float)(p.max_heading_change * (2. * e1 - 1.));
     } else if (a.policy == CA_POLICY_STATIC) {  // goal := pos
@@ -327,32 +330,33 @@ __device__ __forceinline__ void step_take_action(const Params& p, Agent& a, int 
 
 // _compute_rewards (:319-368; sets in_collision) and _check_which_agents_done (:411-439) for one lane, given the result
 // of the all-pairs pass.  gmask = the lanes of this lane's world.  Returns the reward; dn = agent done, over = game_over.
+template <bool kGen = true>
 __device__ __forceinline__ float step_reward_done(const Params& p, Agent& a, bool valid, int i, bool coll, double nearest,
                                                   unsigned gmask, bool& dn, bool& over) {
   // float32 is what leaves the kernel; rounding is monotone, so clipping after the rounding gives the same float as
   // clipping the float64 value first (np.clip at :364) and rounding then
-  float r = (float)p.r_step;
+  float r = p.r_step_f;
   if (valid) {
     if (a.flags & CA_F_AT_GOAL) {
-      if (!(a.flags & CA_F_WAS_AT_GOAL)) r = (float)p.r_goal;  // goal beats collision; in_collision is not set
+      if (!(a.flags & CA_F_WAS_AT_GOAL)) r = p.r_goal_f;  // goal beats collision; in_collision is not set
     } else if (!(a.flags & CA_F_WAS_IN_COLLISION)) {
       if (coll) {
-        r = (float)p.r_coll;
+        r = p.r_coll_f;
         a.flags |= CA_F_IN_COLLISION;
       } else if (nearest <= p.close_range) {
         r = (float)(-0.1 - nearest / 2.);
       }
     }
-    r = fminf(fmaxf(r, (float)p.r_min), (float)p.r_max);
-    if (p.over_mode == CA_OVER_FIRST_AGENT_DONE && i > 0) r = 0.f;  // rewards = rewards[0] (:365-366)
+    r = fminf(fmaxf(r, p.r_min_f), p.r_max_f);
+    if (kGen && p.over_mode == CA_OVER_FIRST_AGENT_DONE && i > 0) r = 0.f;  // rewards = rewards[0] (:365-366)
   } else {
     r = 0.f;
   }
   dn = valid ? (a.flags & CA_F_DONE_MASK) != 0 : true;
   const bool learning = valid && (a.policy == CA_POLICY_LEARNING_GA3C || a.policy == CA_POLICY_LEARNING);
   bool blocks_over;  // this agent keeps the episode alive
-  if (p.over_mode == CA_OVER_ALL_DONE) blocks_over = valid && !dn;
-  else if (p.over_mode == CA_OVER_FIRST_AGENT_DONE) blocks_over = valid && i == 0 && !dn;
+  if (kGen && p.over_mode == CA_OVER_ALL_DONE) blocks_over = valid && !dn;
+  else if (kGen && p.over_mode == CA_OVER_FIRST_AGENT_DONE) blocks_over = valid && i == 0 && !dn;
   else blocks_over = learning && !dn;
   const unsigned alive = __ballot_sync(kFull, blocks_over) & gmask;
   over = alive == 0u;

@@ -66,7 +66,6 @@ struct ca_env {
   int kernel_choice = 1;       // 1 = one-shot specialised kernel, 0 = streaming persistent kernel (ca_step_stream.cuh)
   bool dynamic_sched = true;   // streaming kernel: chunks pulled from the ticket counter (CA_STREAM_STATIC=1: strided)
   unsigned* ticket = nullptr;  // streaming kernel: self-resetting work counter
-  bool store_vec4 = false;     // CA_STORE_MODE=vec4: 128-bit copy-out instead of the TMA bulk store (one-shot kernel)
   bool use_pdl = true;         // programmatic dependent launch for step kernels (CA_DISABLE_PDL=1 turns it off)
   int pipe_min_blocks = 0;     // 0 = default instantiation
   int pipe_grid = 0;
@@ -166,6 +165,8 @@ ca::Params make_params(const ca_env* e) {
   p.close_range = c.getting_close_range;
   p.r_goal = c.reward_at_goal; p.r_coll = c.reward_collision_with_agent; p.r_step = c.reward_time_step;
   p.r_min = c.min_possible_reward; p.r_max = c.max_possible_reward;
+  p.r_goal_f = (float)p.r_goal; p.r_coll_f = (float)p.r_coll; p.r_step_f = (float)p.r_step;
+  p.r_min_f = (float)p.r_min; p.r_max_f = (float)p.r_max;
   p.max_heading_change = c.max_heading_change;
   p.sensing_horizon = c.sensing_horizon;
   p.s = e->s; p.s0 = e->s0; p.consumed = e->consumed;
@@ -273,15 +274,16 @@ int launch_pdl(const void* fn, int grid, size_t smem, cudaStream_t st, ca::Param
 
 int launch_world_kernel(ca_env* e, bool step, ca::Params& p, cudaStream_t st) {
   p.use_bulk_store = (e->bulk_ok && aligned16(p.obs) && (e->tile_floats % 4) == 0) ? 1 : 0;
-  p.warp_store = ((e->tile_floats / kWarps) % 4) == 0 ? 1 : 0;
   int rc;
   // the instantiations with neighbour-index output / finite sensing horizon are only used when asked for
-  const bool dbg = p.sidx != nullptr || std::isfinite(e->cfg.sensing_horizon) || e->M != e->A - 1;
+  // production instantiation: everything the GA3C training configs use; anything else takes the general one
+  const bool dbg = p.sidx != nullptr || std::isfinite(e->cfg.sensing_horizon) || e->M != e->A - 1 || p.cont != nullptr ||
+                   e->cfg.game_over_mode != CA_OVER_ALL_LEARNING_DONE || e->cfg.sort_method != CA_SORT_CLOSEST_FIRST;
   if (step && has_fast_kernel(e) && e->kernel_choice == 0) {
     p.use_bulk_store = e->bulk_ok ? 1 : 0;  // the kernel aligns the tile to the destination's 16-byte phase itself
     rc = launch_pdl(pipe_kernel_ptr(e->A, e->pipe_min_blocks, dbg), e->pipe_grid, e->smem_pipe, st, p, e->use_pdl);
   } else if (step && has_fast_kernel(e)) {
-    if (e->store_vec4 && aligned16(p.obs) && p.warp_store) p.use_bulk_store = 2;
+    p.use_bulk_store = e->bulk_ok ? 1 : 0;  // the kernel aligns the tile to the destination's 16-byte phase itself
     p.prefetch_chunks = e->prefetch_chunks;
     rc = launch_pdl(fast_kernel_ptr(e->A, dbg), e->grid, e->smem_fast, st, p, e->use_pdl);
   } else if (step) {
@@ -371,7 +373,8 @@ int ca_create(const ca_config* cfg, ca_env** out) {
   if (cfg->game_over_mode < 0 || cfg->game_over_mode > CA_OVER_FIRST_AGENT_DONE)
     return fail(CA_ERR_INVALID_ARG, "bad game_over_mode %d", cfg->game_over_mode);
   if (!(cfg->dt > 0)) return fail(CA_ERR_INVALID_ARG, "dt must be > 0");
-  if ((int64_t)cfg->num_worlds * cfg->max_agents * CA_OBS_LEN(cfg->max_others_observed) > (int64_t)1 << 40)
+  if ((int64_t)cfg->num_worlds * cfg->max_agents * CA_OBS_LEN(cfg->max_others_observed) > (int64_t)1 << 40 ||
+      (int64_t)cfg->num_worlds * cfg->max_agents >= (int64_t)1 << 31)
     return fail(CA_ERR_INVALID_ARG, "problem too large");
   int ndev = 0;
   CA_CUDA(cudaGetDeviceCount(&ndev));
@@ -393,7 +396,7 @@ int ca_create(const ca_config* cfg, ca_env** out) {
   const size_t tile_bytes = (((size_t)e->tile_floats * 4 + 127) / 128) * 128;
   const int nkeys = cfg->sort_method == CA_SORT_TIME_TO_IMPACT ? 4 : 3;
   e->smem_bytes = tile_bytes + (size_t)nkeys * e->A * kBlock * sizeof(double);
-  e->smem_fast = tile_bytes;
+  e->smem_fast = (size_t)kWarps * ca::warp_tile_region(e->tile_floats / kWarps);
   const char* nb = getenv("CA_DISABLE_BULK_STORE");
   e->bulk_ok = !(nb && nb[0] == '1');
   const char* fg = getenv("CA_FORCE_GENERIC");
@@ -422,8 +425,6 @@ int ca_create(const ca_config* cfg, ca_env** out) {
   if (kc && (strcmp(kc, "stream") == 0 || strcmp(kc, "pipe") == 0)) e->kernel_choice = 0;
   const char* ss = getenv("CA_STREAM_STATIC");
   e->dynamic_sched = !(ss && ss[0] == '1');
-  const char* sm = getenv("CA_STORE_MODE");
-  e->store_vec4 = sm && strcmp(sm, "vec4") == 0;
   const char* np = getenv("CA_DISABLE_PDL");
   e->use_pdl = !(np && np[0] == '1');
   if (kc && strcmp(kc, "generic") == 0) e->force_generic = true;

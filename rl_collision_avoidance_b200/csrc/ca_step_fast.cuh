@@ -57,10 +57,11 @@ __device__ __forceinline__ void fast_pair_pass(const Params& p, const Agent& a, 
     const bool live = valid && j < n;
     const double rx = xj - a.px, ry = yj - a.py;
     const double d = sqrt(rx * rx + ry * ry);  // l2norm (util.py:8-12)
-    if (kCollide && live) {
+    if (kCollide) {
       const double R = a.rad + rj;
-      if (d <= R) coll = true;
-      if (j > i) nearest = fmin(nearest, d - R);  // only the lower index is updated (:393)
+      const double gap = d - R;
+      coll = coll || (live && d <= R);
+      if (live && j > i && gap < nearest) nearest = gap;  // only the lower index is updated (:393)
     }
     const bool seen = live && !(horizon && d > p.sensing_horizon);
     const double d2o = d - a.rad - rj;
@@ -138,7 +139,7 @@ __device__ __forceinline__ void fast_write_obs_row(const Params& p, const Agent&
       if (rank1[k] >= M) key[k] = INT_MAX;
     count = M;
   }
-  if (p.sort_method == CA_SORT_CLOSEST_LAST) {
+  if (kGen && p.sort_method == CA_SORT_CLOSEST_LAST) {
 #pragma unroll
     for (int k = 0; k < kN; ++k)
       if (key[k] != INT_MAX) key[k] = -key[k];
@@ -192,37 +193,38 @@ __device__ __forceinline__ void fast_write_obs_row(const Params& p, const Agent&
   }
 }
 
-// Warp-level store of the warp's observation rows (its wpw worlds are contiguous in global memory).
-template <int kA>
-__device__ __forceinline__ void fast_store_warp_tile(const Params& p, const float* wtile, long first_world_warp,
-                                                     int lane) {
-  constexpr int wpw = (32 / kA) < 16 ? (32 / kA) : 16;
-  const long worlds_left = (long)p.W - first_world_warp;
-  if (worlds_left <= 0) return;
-  const int nw = worlds_left < wpw ? (int)worlds_left : wpw;
-  const int nfloats = nw * kA * p.L;
-  float* dst = p.obs + (size_t)first_world_warp * kA * p.L;
-  if (p.use_bulk_store == 1 && nw == wpw) {
+// Warp-level store of the warp's observation rows (its wpw worlds are contiguous in global memory).  The rows were
+// assembled at t0 = (16-byte aligned tile base) + shift floats, where shift is the 16-byte phase of dst, so source and
+// destination of the 16-byte-aligned body agree mod 16 for ANY tile size (10 agents x 69 floats included): the body
+// leaves as one TMA bulk store (SASS UBLKCP), at most 3 + 3 head / tail floats as scalar stores.  Returns true when a
+// bulk store was committed: the caller must cp.async.bulk.wait_group.read before the tile is reused or the CTA exits.
+__device__ __forceinline__ int tile_shift(const float* dst) { return (int)((reinterpret_cast<uintptr_t>(dst) >> 2) & 3u); }
+
+__device__ __forceinline__ bool warp_tile_store(const Params& p, float* dst, const float* t0, int shift, int nf, int lane) {
+  const int head = (4 - shift) & 3;
+  const int body = nf >= head ? ((nf - head) & ~3) : 0;
+  if (p.use_bulk_store == 1 && body > 0) {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncwarp();
     if (lane == 0) {
-      asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(wtile)),
-                   "r"(nfloats * 4)
+      asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst + head),
+                   "r"(smem_u32(t0 + head)), "r"(body * 4)
                    : "memory");
       asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-      asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
     }
-    return;
+    if (lane < head) dst[lane] = t0[lane];
+    const int tail = nf - head - body;
+    if (lane < tail) dst[head + body + lane] = t0[head + body + lane];
+    return true;
   }
   __syncwarp();
-  if (p.use_bulk_store == 2 && (nfloats & 3) == 0) {  // 128-bit coalesced copy-out, no wait on the async proxy
-    const float4* s4 = reinterpret_cast<const float4*>(wtile);
-    float4* d4 = reinterpret_cast<float4*>(dst);
-    for (int q = lane; q < nfloats / 4; q += 32) d4[q] = s4[q];
-    return;
-  }
-  for (int q = lane; q < nfloats; q += 32) dst[q] = wtile[q];
+  for (int q = lane; q < nf; q += 32) dst[q] = t0[q];
+  __syncwarp();
+  return false;
 }
+
+// bytes of shared memory per warp for the observation tile: rows + 16 bytes of phase room, 16-byte granular
+__host__ __device__ __forceinline__ int warp_tile_region(int tile_floats) { return ((tile_floats * 4 + 15) / 16) * 16 + 16; }
 
 template <int kA, int kMinBlocks, bool kGen>
 __global__ void __launch_bounds__(kBlock, kMinBlocks) ca_step_kernel(const __grid_constant__ Params p) {
@@ -232,11 +234,12 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks) ca_step_kernel(const __gri
   const int wl = lane / kA;
   const int i = lane - wl * kA;
   const int base = wl * kA;
-  const long first_world_warp = ((long)blockIdx.x * kWarps + warp) * wpw;
-  const long w = first_world_warp + wl;
+  // 32-bit indexing: ca_create refuses W * A >= 2^31
+  const int chunk = blockIdx.x * kWarps + warp;
+  const int first_world_warp = chunk * wpw;
+  const int w = first_world_warp + wl;
   const bool world_ok = wl < wpw && w < p.W;
-  const size_t g = world_ok ? (size_t)w * kA + i : 0;
-  const long chunk = (long)blockIdx.x * kWarps + warp;
+  const unsigned g = world_ok ? (unsigned)w * kA + i : 0u;
   double* const blk = blk_ptr(p.s, chunk);
   pdl_wait();                // nothing produced by the previous kernel is read above this line
   pdl_launch_dependents();
@@ -244,11 +247,13 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks) ca_step_kernel(const __gri
   bool valid = world_ok && i < n;
   const unsigned gmask = (kA >= 32 ? kFull : ((1u << kA) - 1u)) << (base & 31);
 
-  // per-warp tile: rows of the warp's wpw worlds; warp tiles are laid out back to back (no padding) so the
-  // CTA tile is also contiguous
-  float* wtile = reinterpret_cast<float*>(smem_raw) + (size_t)warp * wpw * kA * p.L;
-  float* row = wtile + ((size_t)wl * kA + i) * p.L;
-  int32_t* sidx_row = (p.sidx && world_ok) ? p.sidx + g * p.M : nullptr;
+  // per-warp tile: rows of the warp's wpw worlds, assembled at the 16-byte phase of their destination
+  const int tile_floats = wpw * kA * p.L;
+  float* const dst = p.obs + (size_t)first_world_warp * kA * p.L;
+  const int shift = tile_shift(dst);
+  float* wtile = reinterpret_cast<float*>(smem_raw + warp * warp_tile_region(tile_floats));
+  float* row = wtile + shift + (wl * kA + i) * p.L;
+  int32_t* sidx_row = (kGen && p.sidx && world_ok) ? p.sidx + (size_t)g * p.M : nullptr;
 
   // The state loads do not wait for the agent count: every slot of an existing world is loaded (absent slots hold
   // zeros / stale values and are discarded below), so only ONE DRAM round trip is exposed instead of two.
@@ -260,7 +265,7 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks) ca_step_kernel(const __gri
   }
   if (!valid) { zero_agent(a); act = 0; }
 
-  step_take_action(p, a, act, g, valid);
+  step_take_action<kGen>(p, a, act, g, valid);
 
   Ego e = ego_frame(a.px, a.py, a.gx, a.gy, a.hd);
   OthersLite<kA> o;
@@ -273,7 +278,7 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks) ca_step_kernel(const __gri
     // The grid runs in about two rounds of resident CTAs.  By now this round's own load burst has drained and DRAM is
     // idle while the warps compute: pull the state block and the actions of the chunk that will run in this slot one
     // round later into L2 (TMA bulk prefetch), so the second round does not start with another DRAM burst.
-    const long pc = chunk + p.prefetch_chunks;
+    const int pc = chunk + p.prefetch_chunks;
     if (pc * wpw < p.W) {
       asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(blk_ptr(p.s, pc)), "r"(kBlkReadBytes) : "memory");
       asm volatile("prefetch.global.L2 [%0];" ::"l"(p.actions + (size_t)pc * wpw * kA) : "memory");
@@ -281,7 +286,7 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks) ca_step_kernel(const __gri
   }
 
   bool dn, over;
-  const float r = step_reward_done(p, a, valid, i, coll, nearest, gmask, dn, over);
+  const float r = step_reward_done<kGen>(p, a, valid, i, coll, nearest, gmask, dn, over);
   if (world_ok) {
     p.reward[g] = r;
     p.done[g] = dn ? 1 : 0;
@@ -293,7 +298,7 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks) ca_step_kernel(const __gri
   // here instead of occupying registers through the ranking / row code.
   if (!__any_sync(kFull, do_reset)) {
     if (valid) store_agent(blk, lane, a, a.policy == CA_POLICY_STATIC, false);
-    fast_write_obs_row<kA, kGen>(p, a, e, world_ok, valid, nm1, i, base, o, row, sidx_row, wtile, wpw * kA * p.L);
+    fast_write_obs_row<kA, kGen>(p, a, e, world_ok, valid, nm1, i, base, o, row, sidx_row, wtile, (tile_floats + 7) & ~3);
   } else {
     // DummyVecEnv semantics: worlds that finished reload their injected initial state and observe again;
     // the other worlds of the warp observe their post-step state.
@@ -311,11 +316,15 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks) ca_step_kernel(const __gri
     double n_unused;
     const int nm1r = others_bound<kA>(n);
     fast_pair_pass<kA, false, kGen>(p, a, e, valid, n, nm1r, i, base, o, c_unused, n_unused);
-    fast_write_obs_row<kA, kGen>(p, a, e, world_ok, valid, nm1r, i, base, o, row, sidx_row, wtile, wpw * kA * p.L);
+    fast_write_obs_row<kA, kGen>(p, a, e, world_ok, valid, nm1r, i, base, o, row, sidx_row, wtile, (tile_floats + 7) & ~3);
   }
 
-  if (p.warp_store) fast_store_warp_tile<kA>(p, wtile, first_world_warp, lane);
-  else store_tile(p, reinterpret_cast<float*>(smem_raw), (long)blockIdx.x * kWarps * wpw, tid);
+  const int worlds_left = p.W - first_world_warp;
+  if (worlds_left > 0) {
+    const int nf = (worlds_left < wpw ? worlds_left : wpw) * kA * p.L;
+    if (warp_tile_store(p, dst, wtile + shift, shift, nf, lane) && lane == 0)
+      asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // the tile must outlive the store's reads
+  }
 }
 
 }  // namespace ca

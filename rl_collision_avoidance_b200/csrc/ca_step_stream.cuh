@@ -54,7 +54,7 @@ constexpr int kStageBytes = kBlkReadBytes;  // one warp's state stage = the part
 
 // bytes of shared memory one warp of the streaming kernel needs: [state stage][tile + 16 B phase room][mbarrier]
 __host__ __device__ __forceinline__ int stream_warp_region(int tile_floats) {
-  return kStageBytes + ((tile_floats * 4 + 15) / 16) * 16 + 16 + 16;
+  return kStageBytes + warp_tile_region(tile_floats) + 16;
 }
 
 template <int kA, int kMinBlocks, bool kGen>
@@ -92,8 +92,8 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks) ca_step_stream_kernel(cons
   // loads of chunk c: the whole state block by ONE bulk copy into the stage, the caller's action into a register
   int pf_act = 0;
   auto prefetch = [&](int c) {
-    const long w = (long)c * wpw + wl;
-    pf_act = (lane_used && w < p.W) ? p.actions[(size_t)w * kA + i] : 0;
+    const int w = c * wpw + wl;
+    pf_act = (lane_used && w < p.W) ? p.actions[(unsigned)w * kA + i] : 0;
     if (lane == 0) {
       mbar_arrive_expect_tx(bar, kBlkReadBytes);
       tma_load_1d(stage, blk_ptr(p.s, c), kBlkReadBytes, bar);
@@ -115,12 +115,12 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks) ca_step_stream_kernel(cons
   draw();
 
   while (true) {
-    const long first_world = (long)c * wpw;
-    const long w = first_world + wl;
+    const int first_world = c * wpw;   // 32-bit indexing: ca_create refuses W * A >= 2^31
+    const int w = first_world + wl;
     const bool world_ok = lane_used && w < p.W;
-    const size_t g = world_ok ? (size_t)w * kA + i : 0;
+    const unsigned g = world_ok ? (unsigned)w * kA + i : 0u;
     double* const blk = blk_ptr(p.s, c);
-    int32_t* sidx_row = (kGen && p.sidx && world_ok) ? p.sidx + g * p.M : nullptr;
+    int32_t* sidx_row = (kGen && p.sidx && world_ok) ? p.sidx + (size_t)g * p.M : nullptr;
 
     // the chunk's block has landed in the stage (padded blocks make partial last chunks loadable too)
     mbar_wait(bar, parity);
@@ -148,7 +148,7 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks) ca_step_stream_kernel(cons
       draw();
     }
 
-    step_take_action(p, a, act, g, valid);
+    step_take_action<kGen>(p, a, act, g, valid);
 
     Ego e = ego_frame(a.px, a.py, a.gx, a.gy, a.hd);
     OthersLite<kA> o;
@@ -158,7 +158,7 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks) ca_step_stream_kernel(cons
     fast_pair_pass<kA, true, kGen>(p, a, e, valid, n, nm1, i, base, o, coll, nearest);
 
     bool dn, over;
-    const float r = step_reward_done(p, a, valid, i, coll, nearest, gmask, dn, over);
+    const float r = step_reward_done<kGen>(p, a, valid, i, coll, nearest, gmask, dn, over);
     if (world_ok) {
       p.reward[g] = r;
       p.done[g] = dn ? 1 : 0;
@@ -168,7 +168,7 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks) ca_step_stream_kernel(cons
 
     // observation rows are assembled at the destination's 16-byte phase
     float* const dst = p.obs + (size_t)first_world * kA * p.L;
-    const int shift = (int)((reinterpret_cast<uintptr_t>(dst) >> 2) & 3u);
+    const int shift = tile_shift(dst);
     float* const row = wtile + shift + ((size_t)wl * kA + i) * p.L;
 
     // the tile still feeds the previous chunk's bulk store until that store has read it
@@ -200,31 +200,10 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks) ca_step_stream_kernel(cons
       fast_write_obs_row<kA, kGen>(p, a, e, world_ok, valid, nm1r, i, base, o, row, sidx_row, wtile, (tile_floats + 7) & ~3);
     }
 
-    // ---- observation tile -> global
-    const long worlds_left = (long)p.W - first_world;
-    const int nf = (worlds_left < wpw ? (int)worlds_left : wpw) * kA * p.L;
-    const int head = (4 - shift) & 3;
-    const int body = nf >= head ? ((nf - head) & ~3) : 0;
-    if (p.use_bulk_store && body > 0) {
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      __syncwarp();
-      const float* t0 = wtile + shift;
-      if (lane == 0) {
-        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst + head),
-                     "r"(smem_u32(t0 + head)), "r"(body * 4)
-                     : "memory");
-        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-      }
-      if (lane < head) dst[lane] = t0[lane];
-      const int tail = nf - head - body;
-      if (lane < tail) dst[head + body + lane] = t0[head + body + lane];
-      store_pending = true;
-    } else {
-      __syncwarp();
-      const float* t0 = wtile + shift;
-      for (int q = lane; q < nf; q += 32) dst[q] = t0[q];
-      __syncwarp();
-    }
+    // ---- observation tile -> global (the wait for the store is deferred to the next chunk)
+    const int worlds_left = p.W - first_world;
+    const int nf = (worlds_left < wpw ? worlds_left : wpw) * kA * p.L;
+    store_pending = warp_tile_store(p, dst, wtile + shift, shift, nf, lane);
     if (!more) break;
     c = nxt;
   }
