@@ -1,30 +1,37 @@
 #!/usr/bin/env python
 """bench.py — agent-steps/s of the fused env.step() kernel on B200 (BASELINE.json configs[1]).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload phase1|phase2|ragged]
 
 One "step" = one pass of the hot path (one fused kernel launch) over one batch of W worlds x A agents.
 Workload (config.workload): 4 agents x 65 536 worlds per GPU, random-policy discrete actions, auto-reset on
 game_over (DummyVecEnv semantics) so worlds keep running.  N>1 (torchrun): worlds shard across ranks with no
-data-path collective (weak scaling); NCCL is used for the barrier and the max-over-ranks reduction only.
+data-path collective in the step (weak scaling); NCCL carries the barrier, the max-over-ranks reduction and — in the
+`train_loop` extra workload — the gradient all-reduce of the GA3C learner.
 
-Timing: device-side CUDA events on the launching stream, W >= 3 warm-up steps, barrier + synchronize on
-both sides, max over ranks.  L2: steps rotate over a ring of R independent world sets whose combined
-working set (state + observations) exceeds the 126 MB L2, so no step finds its data in L2.
+Timing: device-side CUDA events on the launching stream, W >= 3 warm-up steps, barrier + synchronize on both sides,
+max over ranks.  Every one of the K timed steps is replayed from a CUDA graph (whole graphs of G steps plus one graph
+of K mod G steps): no eager launch and no in-process polling thread runs inside the timed region; clocks / throttle
+reasons are sampled by a CHILD process through NVML while the timed regions run.  L2: steps rotate over a ring of R
+independent world sets whose combined working set exceeds the 126 MB L2, so no step finds its data in L2.
   value      K steps replayed from CUDA graphs, inputs resident in HBM
-  e2e        the same K steps through ca_step_host: actions from pinned host memory (H2D), observations,
-             rewards, done and game_over back to pinned host memory (D2H), synchronous per step
-  roofline   algorithmic bytes per launch (100 + 28*M bytes per live agent-step) / mean launch
-             duration from the same CUDA events; peak = MEASURED_PEAKS.json hbm_gbs
-  cpu_baseline / --impl reference   the C oracle port (oracle/ca_oracle.c) on all host cores — the only places
-             where bench.py executes oracle/; it is the reported baseline, never the thing measured as "ours"
+  e2e        the same metric through ca_step_host_async / ca_step_host_wait: actions from pinned host memory (H2D),
+             observations, rewards, done and game_over back to pinned host memory (D2H) every step
+  roofline   algorithmic bytes per launch (100 + 28*M bytes per live agent-step) / mean launch duration from
+             the same CUDA events; peak = MEASURED_PEAKS.json hbm_gbs; traffic = steady-state DRAM bytes per launch (ncu)
+  cpu_baseline            the C oracle port (oracle/ca_oracle.c) on all host cores, same workload (kind "port")
+  cpu_baseline_reference  the UNMODIFIED reference Python/NumPy env staged under oracle/_ref/ (kind "reference")
+  config.extra_workloads  BASELINE configs[2] (env half and full GA3C rollout), configs[3] (ragged) and the GA3C training
+             loop of configs[4] on this rank count, each with its own numbers (sub-records, not the headline)
+  --impl reference        the reference arm: the oracle port on all host threads — the only places where bench.py
+             executes oracle/; it is the reported baseline, never the thing measured as "ours"
 """
 import argparse
 import json
 import os
-import statistics
+import signal
+import subprocess
 import sys
-import threading
 import time
 
 REPO = os.path.dirname(os.path.abspath(__file__))
@@ -33,32 +40,35 @@ if REPO not in sys.path:
 
 import numpy as np  # noqa: E402
 
-# name -> (agent slots per world, worlds per GPU, ragged agent counts, config.workload text, one-shot kernel occupancy)
+# name -> (agent slots per world, worlds per GPU, ragged agent counts, config.workload text)
 WORKLOADS = {
     "phase1": (4, 65536, False,
-               "4-agent x 65536 worlds vectorised env.step, random-policy actions, auto-reset (BASELINE configs[1])", 7),
+               "4-agent x 65536 worlds vectorised env.step, random-policy actions, auto-reset (BASELINE configs[1])"),
     "phase2": (10, 16384, False,
                "10-agent x 16384 worlds vectorised env.step only (the env half of BASELINE configs[2]), random-policy "
-               "actions, auto-reset", 5),
+               "actions, auto-reset"),
     "ragged": (10, 32768, True,
                "variable 2-10 agents per world (ragged, n_w = 2 + w mod 9, mean 6 live agents) x 32768 worlds, random-policy "
-               "actions, auto-reset (BASELINE configs[3]); agent-steps count live agents only", 5),
+               "actions, auto-reset (BASELINE configs[3]); agent-steps count live agents only"),
 }
 AGENTS = 4
 WORLDS_PER_GPU = 65536
 OTHERS = AGENTS - 1
 RAGGED = False
-MINBLOCKS = 7
 ALG_BYTES_PER_AGENT_STEP = 100 + 28 * OTHERS      # 100 + 28*M bytes; 184 B at M = 3, 352 B at M = 9
 WORKLOAD = WORKLOADS["phase1"][3]
+WORKLOAD_NAME = "phase1"
+STATE_BLOCK_BYTES = 2304                           # csrc/ca_kernels.cuh kBlkBytes
+FALLBACK_HBM_GBS = 6650.0                          # /opt/skills/guides/B200_PROFILING.md fallback
 
 
 def select_workload(name):
-    """The default (phase1 = BASELINE configs[1]) is the bench line the driver records; the others are extra lines."""
-    global AGENTS, WORLDS_PER_GPU, OTHERS, RAGGED, MINBLOCKS, ALG_BYTES_PER_AGENT_STEP, WORKLOAD
-    AGENTS, WORLDS_PER_GPU, RAGGED, WORKLOAD, MINBLOCKS = WORKLOADS[name]
+    """The default (phase1 = BASELINE configs[1]) is the bench line the driver records; the others are extra records."""
+    global AGENTS, WORLDS_PER_GPU, OTHERS, RAGGED, ALG_BYTES_PER_AGENT_STEP, WORKLOAD, WORKLOAD_NAME
+    AGENTS, WORLDS_PER_GPU, RAGGED, WORKLOAD = WORKLOADS[name]
     OTHERS = AGENTS - 1
     ALG_BYTES_PER_AGENT_STEP = 100 + 28 * OTHERS
+    WORKLOAD_NAME = name
 
 
 def live_agents(worlds):
@@ -70,7 +80,6 @@ def agent_counts(worlds):
     if RAGGED:
         return (2 + (np.arange(worlds) % 9)).astype(np.int32)
     return None
-FALLBACK_HBM_GBS = 6650.0                          # /opt/skills/guides/B200_PROFILING.md fallback
 
 
 def measured_peak():
@@ -82,80 +91,97 @@ def measured_peak():
         return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
 
 
-def ncu_traffic_per_launch():
-    """dram bytes per launch of the step kernel from the committed ncu --set full capture, or None."""
+def step_kernel_name():
+    kind = os.environ.get("CA_STEP_KERNEL", "oneshot")
+    name = {"stream": "ca_step_stream_kernel", "pipe": "ca_step_stream_kernel", "generic": "ca_world_kernel"}.get(kind, "ca_step_kernel")
+    return "ca::%s<%d, ...>" % (name, AGENTS) if name != "ca_world_kernel" else "ca::ca_world_kernel<true>"
+
+
+def ncu_traffic_per_launch(workload):
+    """Steady-state DRAM bytes per launch of the step kernel (ncu --cache-control none over consecutive rotated launches,
+    profiles/traffic.json), or None when no capture of this workload is committed."""
     p = os.path.join(REPO, "profiles", "traffic.json")
     try:
         with open(p) as f:
-            return float(json.load(f)["ca_world_kernel_step"]["dram_bytes_per_launch"])
+            return float(json.load(f)["ca_step_kernel"][workload]["dram_bytes_per_launch"])
     except Exception:
         return None
 
 
-class ClockSampler(threading.Thread):
-    """Polls SM clock / throttle reasons through NVML every ~2 ms while the timed regions run."""
-
-    def __init__(self, index):
-        threading.Thread.__init__(self, daemon=True)
-        self.index = index
-        self.samples = []
-        self.reasons = set()
-        self.max_mhz = None
-        self._halt = threading.Event()
-        self.ok = False
+# ---------------------------------------------------------------------------------------------- clocks (child process)
+_SAMPLER_SRC = r'''
+import json, signal, sys, time
+idx = int(sys.argv[1]); period = float(sys.argv[2])
+samples, reasons, stop = [], set(), [False]
+def _term(*a): stop[0] = True
+signal.signal(signal.SIGTERM, _term); signal.signal(signal.SIGINT, _term)
+out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+try:
+    import pynvml as nv
+    nv.nvmlInit()
+    h = nv.nvmlDeviceGetHandleByIndex(idx)
+    out["sm_max_mhz"] = int(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+    names = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap",
+             0x80: "hw_power_brake_slowdown"}
+    print("ready", flush=True)
+    while not stop[0]:
         try:
-            import pynvml
-            pynvml.nvmlInit()
-            self.nv = pynvml
-            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
-            self.max_mhz = int(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
-            self.ok = True
+            mhz = int(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+            util = int(nv.nvmlDeviceGetUtilizationRates(h).gpu)
+            mask = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(h))
+            samples.append((mhz, util))
+            for bit, name in names.items():
+                if mask & bit: reasons.add(name)
         except Exception:
-            self.ok = False
+            pass
+        time.sleep(period)
+except Exception as e:
+    out["error"] = repr(e)
+    print("ready", flush=True)
+busy = [m for m, u in samples if u > 0] or [m for m, u in samples]
+if busy:
+    busy.sort(); out["sm_mhz"] = busy[len(busy) // 2]
+out["reasons"] = sorted(reasons); out["samples"] = len(samples); out["samples_under_load"] = len([1 for m, u in samples if u > 0])
+print(json.dumps(out), flush=True)
+'''
 
-    def run(self):
-        if not self.ok:
-            return
-        nv = self.nv
-        names = {
-            getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8): "hw_slowdown",
-            getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
-            getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
-            getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4): "sw_power_cap",
-            getattr(nv, "nvmlClocksThrottleReasonHwPowerBrakeSlowdown", 0x80): "hw_power_brake_slowdown",
-        }
-        while not self._halt.is_set():
-            try:
-                mhz = int(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
-                util = nv.nvmlDeviceGetUtilizationRates(self.h).gpu
-                mask = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
-                self.samples.append((mhz, util))
-                for bit, name in names.items():
-                    if mask & bit:
-                        self.reasons.add(name)
-            except Exception:
-                pass
-            time.sleep(0.002)
+
+class ClockSampler(object):
+    """SM clock / throttle reasons polled through NVML by a child process (no thread, no GIL contention in this one)."""
+
+    def __init__(self, index, period=0.01):
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen([sys.executable, "-c", _SAMPLER_SRC, str(index), str(period)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.proc.stdout.readline()   # "ready": NVML is initialised, sampling has started
+        except Exception:
+            self.proc = None
 
     def stop(self):
-        self._halt.set()
-        if self.is_alive():
-            self.join(timeout=2)
-        if not self.samples:
-            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": 0}
-        mhz = [m for m, _ in self.samples]
-        return {"sm_mhz": statistics.median(mhz), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
-                "samples": len(mhz)}
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        try:
+            self.proc.send_signal(signal.SIGTERM)
+            out, _ = self.proc.communicate(timeout=10)
+            return json.loads(out.strip().split("\n")[-1])
+        except Exception:
+            try:
+                self.proc.kill()
+            except Exception:
+                pass
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
 
 
+# ---------------------------------------------------------------------------------------------- inputs / CPU arms
 def make_inputs(rank, n_sets, worlds):
     from rl_collision_avoidance_b200.scenarios import random_worlds
     rng = np.random.default_rng(20261017 + 1000 * rank)
     return [random_worlds(worlds, AGENTS, rng, num_agents=agent_counts(worlds)) for _ in range(n_sets)], rng
 
 
-def cpu_baseline_run(seconds, worlds):
-    """C oracle port on all host cores, bounded sample of the same workload."""
+def port_run(worlds, steps=None, seconds=None, warmup=1):
+    """The C oracle port on all host cores over `worlds` worlds: `steps` steps, or as many as fit in `seconds`."""
     from oracle.ca_oracle import OracleEnv
     from rl_collision_avoidance_b200 import _abi
     cores = os.cpu_count() or 1
@@ -165,19 +191,37 @@ def cpu_baseline_run(seconds, worlds):
     env.set_world_state(init, nag)
     env.reset()
     acts = rng.integers(0, 11, (8, worlds, AGENTS)).astype(np.int32)
-    env.step(acts[0], nthreads=cores)  # warm-up
+    for k in range(max(1, warmup)):
+        env.step(acts[k % 8], nthreads=cores)
     n, t0 = 0, time.perf_counter()
     while True:
         env.step(acts[n % 8], nthreads=cores)
         n += 1
         el = time.perf_counter() - t0
-        if el >= seconds and n >= 3:
+        if (steps is not None and n >= steps) or (steps is None and el >= seconds and n >= 3):
             break
     env.close()
+    return n, el, cores
+
+
+def cpu_baseline_run(seconds):
+    """cpu_baseline: the port over the SAME workload as the GPU line and the reference arm (all worlds, every step)."""
+    worlds = WORLDS_PER_GPU
+    n, el, cores = port_run(worlds, seconds=seconds)
     return {"value": n * live_agents(worlds) / el, "unit": "agent-steps/s", "cores": cores, "kind": "port",
             "sample": "oracle/ca_oracle.c (C restatement of the reference env.step), %d pthreads, %d worlds x %d agents, "
-                      "%d steps in %.1f s; the reference's own Python/NumPy env runs ~3.5k agent-steps/s per core "
-                      "(BASELINE.md §2) and cannot travel to the GPU box" % (cores, worlds, AGENTS, n, el)}
+                      "%d steps in %.1f s" % (cores, worlds, AGENTS, n, el)}
+
+
+def cpu_reference_run(seconds):
+    """The unmodified reference env on all host cores (oracle/ref_bench.py), or a one-line reason why not."""
+    try:
+        from oracle import ref_bench
+        if not ref_bench.available():
+            return {"unavailable": "oracle/_ref/ not staged (oracle/stage_ref.py runs where /root/reference exists)"}
+        return ref_bench.run(agents=AGENTS, seconds=seconds)
+    except Exception as e:   # a reported baseline must never take the bench line down
+        return {"unavailable": "reference env failed to run: %r" % (e,)}
 
 
 def run_reference_arm(args):
@@ -185,29 +229,14 @@ def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    from oracle.ca_oracle import OracleEnv
-    from rl_collision_avoidance_b200 import _abi
-    cores = os.cpu_count() or 1
     worlds = WORLDS_PER_GPU
-    (sets, rng) = make_inputs(0, 1, worlds)
-    init, nag = sets[0]
-    env = OracleEnv(_abi.default_config(worlds, AGENTS, auto_reset=1))
-    env.set_world_state(init, nag)
-    env.reset()
-    acts = rng.integers(0, 11, (8, worlds, AGENTS)).astype(np.int32)
-    for k in range(args.warmup):
-        env.step(acts[k % 8], nthreads=cores)
-    t0 = time.perf_counter()
-    for k in range(args.steps):
-        env.step(acts[k % 8], nthreads=cores)
-    el = time.perf_counter() - t0
-    env.close()
-    value = args.steps * live_agents(worlds) / el
+    n, el, cores = port_run(worlds, steps=args.steps, warmup=args.warmup)
+    value = n * live_agents(worlds) / el
     sample = ("oracle/ca_oracle.c port of the reference env.step on %d host threads; each step = all %d worlds x %d agents"
               % (cores, worlds, AGENTS))
     line = {
         "impl": "reference", "metric": "agent-steps/sec", "value": value, "unit": "agent-steps/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * el / args.steps, "higher_is_better": True,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * el / n, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": WORKLOAD, "worlds": worlds, "agents_per_world": AGENTS},
         "cpu_baseline": {"value": value, "unit": "agent-steps/s", "cores": cores, "kind": "port", "sample": sample},
@@ -217,11 +246,199 @@ def run_reference_arm(args):
     print(json.dumps(line), flush=True)
 
 
+# ---------------------------------------------------------------------------------------------- device-resident steps
+class GraphedSteps(object):
+    """R independent world sets stepped round-robin; G = 2R consecutive steps captured in one CUDA graph, plus one
+    graph per distinct tail length on demand, so that ANY number of steps is replayed without an eager launch."""
+
+    def __init__(self, sets, device, seed):
+        import torch
+        from rl_collision_avoidance_b200 import _abi
+        from rl_collision_avoidance_b200.vec_env import VecCollisionAvoidanceEnv
+        self.torch = torch
+        W, A = WORLDS_PER_GPU, AGENTS
+        self.R = len(sets)
+        self.G = 2 * self.R
+        self.envs = []
+        for init, nag in sets:
+            e = VecCollisionAvoidanceEnv(_abi.default_config(W, A, auto_reset=1, device=device))
+            e.set_world_state(init, nag)
+            e.reset()
+            self.envs.append(e)
+        gen = torch.Generator(device="cuda")
+        gen.manual_seed(seed)
+        self.actions = [torch.randint(0, 11, (W, A), dtype=torch.int32, device="cuda", generator=gen) for _ in range(self.G)]
+        self.stream = torch.cuda.Stream()
+        self.graphs = {}
+        with torch.cuda.stream(self.stream):
+            for k in range(self.G):                       # lazy init before capture
+                self._eager(k)
+            self.stream.synchronize()
+        self._graph(self.G)
+
+    def _eager(self, k):
+        self.envs[k % self.R].step(self.actions[k % self.G])
+
+    def _graph(self, n):
+        torch = self.torch
+        if n not in self.graphs:
+            with torch.cuda.stream(self.stream):
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, stream=self.stream):
+                    for k in range(n):
+                        self._eager(k)
+                g.replay()                                # upload + first run outside any timed region
+                self.stream.synchronize()
+            self.graphs[n] = g
+        return self.graphs[n]
+
+    def run(self, steps, barrier=None):
+        """Replays exactly `steps` steps; returns the device time in ms (CUDA events on the launching stream)."""
+        torch = self.torch
+        n_graph, n_tail = steps // self.G, steps % self.G
+        full = self._graph(self.G)
+        tail = self._graph(n_tail) if n_tail else None
+        with torch.cuda.stream(self.stream):
+            if barrier:
+                barrier()
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ev0.record(self.stream)
+            for _ in range(n_graph):
+                full.replay()
+            if tail is not None:
+                tail.replay()
+            ev1.record(self.stream)
+            self.stream.synchronize()
+            if barrier:
+                barrier()
+        return ev0.elapsed_time(ev1)
+
+    def close(self):
+        self.graphs.clear()
+        for e in self.envs:
+            e.close()
+        self.envs = []
+        self.torch.cuda.empty_cache()
+
+
+def env_workload_record(name, rank, local_rank, steps, barrier, max_over_ranks, world_size):
+    """One extra env.step workload (device-resident, same method as `value`): a sub-record with its own roofline."""
+    saved = WORKLOAD_NAME
+    select_workload(name)
+    try:
+        sets, _ = make_inputs(rank, 6, WORLDS_PER_GPU)
+        gs = GraphedSteps(sets, local_rank, 4321 + rank)
+        gs.run(2 * gs.G)
+        ms = max_over_ranks(gs.run(steps, barrier))
+        gs.close()
+        live = live_agents(WORLDS_PER_GPU)
+        peak, _ = measured_peak()
+        launch_ms = ms / steps
+        achieved = ALG_BYTES_PER_AGENT_STEP * live / (launch_ms * 1e-3) / 1e9
+        return {"workload": WORKLOAD, "value": world_size * live * steps / (ms * 1e-3), "unit": "agent-steps/s",
+                "ms_per_step": launch_ms, "steps": steps, "worlds_per_gpu": WORLDS_PER_GPU, "agent_slots": AGENTS,
+                "live_agents_per_step": live,
+                "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                             "algorithmic_bytes_per_launch": ALG_BYTES_PER_AGENT_STEP * live,
+                             "traffic": ncu_traffic_per_launch(name), "kernel": step_kernel_name()}}
+    finally:
+        select_workload(saved)
+
+
+def rollout_record(cls, worlds, steps, fixed_agents, local_rank, max_over_ranks, world_size):
+    """BASELINE configs[2]: the GA3C actor -> predictor loop on the device (row plan, fused NetworkVP forward + action
+    sampling, env step, statistics, experience bookkeeping, row gather, scenario refresh), random-init weights."""
+    import torch
+    from rl_collision_avoidance_b200.ga3c import Config as cfgmod
+    from rl_collision_avoidance_b200.ga3c.NetworkVP_rnn import NetworkVP_rnn
+    from rl_collision_avoidance_b200.ga3c.rollout import GpuRollout
+    from rl_collision_avoidance_b200.scenarios import random_worlds
+    cfg = getattr(cfgmod, cls)()
+    cfgmod.set_config(cfg)
+    try:
+        A = cfg.MAX_NUM_AGENTS_IN_ENVIRONMENT
+        rng = np.random.default_rng(7 + local_rank)
+        init, nag = random_worlds(worlds, A, rng)
+        model = NetworkVP_rnn("cuda:%d" % local_rank, "network", 11, seed=0)
+        ro = GpuRollout(cfg, model, worlds, init, nag, device=local_rank, seed=1 + local_rank)
+        sc = ro.env.scenario_config(cfg.TEST_CASE_ARGS)
+        if fixed_agents:
+            sc.min_agents = sc.max_agents = A
+        ro.env.generate_scenarios(sc, 5, only_consumed=False)
+        ro.env.reset(out_obs=ro.rec.obs_slot(ro.t))
+        ro.attach_scenario_generator(sc, 5)
+        for _ in range(8):
+            ro.step()
+            ro.rec.discard()
+        o = ro.rec.obs_slot(ro.t)
+        live = float((o[..., 5] > 0).sum())
+        learning = float((o[..., 0] != 0).sum())
+        torch.cuda.synchronize()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        rows = 0
+        ev0.record()
+        for k in range(steps):
+            ro.step()
+            if k % 8 == 7:
+                rows += int(ro.rec.take()[0].shape[0])
+        ev1.record()
+        torch.cuda.synchronize()
+        ms = max_over_ranks(ev0.elapsed_time(ev1))
+        o = ro.rec.obs_slot(ro.t)
+        live = 0.5 * (live + float((o[..., 5] > 0).sum()))
+        learning = 0.5 * (learning + float((o[..., 0] != 0).sum()))
+        ro.close()
+        return {"workload": "%s GA3C rollout, %d worlds x %d agent slots per GPU, %s, fused tcgen05 predictor "
+                            "(BASELINE configs[2])" % (cls, worlds, A, "all agents present" if fixed_agents else
+                                                       "training mix (2..A agents, 5/90/5 policies)"),
+                "value": world_size * live * steps / (ms * 1e-3), "unit": "live agent-steps/s", "ms_per_step": ms / steps,
+                "steps": steps, "live_agents_per_step": live, "learning_agents_per_step": learning,
+                "training_rows_per_s": world_size * rows / (ms * 1e-3)}
+    finally:
+        cfgmod.set_config(None)
+
+
+def train_loop_record(seconds, worlds, local_rank, world_size):
+    """BASELINE configs[4] on this rank count: Server.main (TrainPhase1) with `worlds` worlds per GPU — rollout, A3C
+    updates, and (N > 1) the gradient all-reduce over NCCL."""
+    import torch
+    os.environ["GYM_CONFIG_CLASS"] = "TrainPhase1"
+    os.environ["GA3C_GPU_NUM_WORLDS"] = str(worlds)
+    os.environ.setdefault("GA3C_CHECKPOINT_DIR", "/tmp/ga3c_bench_ckpt")
+    from rl_collision_avoidance_b200.ga3c import Config as cfgmod
+    from rl_collision_avoidance_b200.ga3c.Server import Server
+    cfgmod.set_config(None)
+    cfg = cfgmod.get_config()
+    cfg.SAVE_MODELS = False
+    cfg.EPISODES = 10 ** 12
+    try:
+        srv = Server(cfg, device=local_rank)
+        srv.main(max_steps=8, quiet=True)          # lazy init, allocator warm-up
+        f0, s0 = srv.stats.total_frame_count, srv.training_step
+        res = srv.main(max_seconds=seconds, quiet=True)
+        n_param = sum(p.numel() for p in srv.model.net.parameters())
+        frames = srv.stats.total_frame_count - f0
+        rec = {"workload": "Server.main TrainPhase1 loop (BASELINE configs[4] at %d GPU%s): %d worlds x 4 agents per GPU, "
+                           "fused predictor rollout + A3C updates" % (world_size, "s" if world_size > 1 else "", worlds),
+               "frames_per_s": frames / res["seconds"], "env_steps_per_s": res["steps"] / res["seconds"],
+               "optimiser_steps_per_s": (srv.training_step - s0) / res["seconds"], "seconds": res["seconds"],
+               "rows_per_optimiser_step": srv.train_batch_rows() * world_size,
+               "learning_rate": srv.model.learning_rate, "lr_scale": str(cfg.GPU_LR_SCALE),
+               "allreduce_bytes_per_optimiser_step": 4 * n_param if world_size > 1 else 0,
+               "collective": "NCCL all_reduce of the flat fp32 gradient" if world_size > 1 else "none (1 GPU)",
+               "episodes": res["episodes"], "rolling_score": srv.stats.roll_reward_log}
+        srv.rollout.close()
+        return rec
+    finally:
+        cfgmod.set_config(None)
+        torch.cuda.empty_cache()
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
     from rl_collision_avoidance_b200 import _abi, _lib
-    from rl_collision_avoidance_b200.vec_env import HostVecEnv, VecCollisionAvoidanceEnv
+    from rl_collision_avoidance_b200.vec_env import HostVecEnv
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -249,62 +466,25 @@ def run_ours(args):
         return float(t.item())
 
     W, A, K, WU = WORLDS_PER_GPU, AGENTS, args.steps, max(args.warmup, 3)
-    R = 6          # ring of world sets: 6 x (21 MB state + 28 MB obs + ...) ~ 300 MB >> 126 MB L2
-    G = 2 * R      # steps per captured CUDA graph
-    T = G          # ring of action tensors
+    R = 6          # ring of world sets: 6 x (19 MB state + 28 MB obs + ...) ~ 300 MB >> 126 MB L2
     sets, rng = make_inputs(rank, R, W)
-    envs = []
-    for init, nag in sets:
-        e = VecCollisionAvoidanceEnv(_abi.default_config(W, A, auto_reset=1, device=local_rank))
-        e.set_world_state(init, nag)
-        e.reset()
-        envs.append(e)
-    gen = torch.Generator(device="cuda")
-    gen.manual_seed(1234 + rank)
-    actions = [torch.randint(0, 11, (W, A), dtype=torch.int32, device="cuda", generator=gen) for _ in range(T)]
-    bytes_per_set = 2 * (W // max(1, min(32 // A, 16))) * 2304 + W * A * 4 + W * A * _abi.obs_len(OTHERS) * 4 + W * A * 9   # state blocks x2, actions, obs, outputs
-
-    def eager_step(k):
-        envs[k % R].step(actions[k % T])
-
-    stream = torch.cuda.Stream()
+    gs = GraphedSteps(sets, local_rank, 1234 + rank)
+    G = gs.G
+    bytes_per_set = 2 * (W // max(1, min(32 // A, 16))) * STATE_BLOCK_BYTES + W * A * 4 + W * A * _abi.obs_len(OTHERS) * 4 + W * A * 9
     sampler = ClockSampler(local_rank)
-    with torch.cuda.stream(stream):
-        for k in range(G):                       # lazy init before capture
-            eager_step(k)
-        stream.synchronize()
-        graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(graph, stream=stream):
-            for k in range(G):
-                eager_step(k)
-        n_graph, n_tail = K // G, K % G
-        for _ in range(max(1, (WU + G - 1) // G)):   # warm-up (>= W steps)
-            graph.replay()
-        barrier()
-        sampler.start()
-        launches0 = sum(e.handle.launch_count for e in envs)
-        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        ev0.record(stream)
-        for _ in range(n_graph):
-            graph.replay()
-        for k in range(n_tail):
-            eager_step(k)
-        ev1.record(stream)
-        stream.synchronize()
-        barrier()
-        dev_ms = ev0.elapsed_time(ev1)
-    # graph replays launch the captured kernels without going through ca_step: count them explicitly
-    gpu_launches = n_graph * G + (sum(e.handle.launch_count for e in envs) - launches0)
-    dev_ms = max_over_ranks(dev_ms)
+    launches0 = sum(e.handle.launch_count for e in gs.envs)
+    gs.run(max(WU, G))                           # warm-up (>= W steps), same replay path as the timed region
+    gs.run(K)                                    # one untimed pass of exactly the timed pattern (graphs uploaded, clocks up)
+    dev_ms = max_over_ranks(gs.run(K, barrier))  # THE timed region: K steps, graph replays only
+    eager_launches = sum(e.handle.launch_count for e in gs.envs) - launches0
+    gpu_launches = K                             # kernels launched inside the timed region (all from graph replays)
     agent_steps = K * live_agents(W)
     value = world_size * agent_steps / (dev_ms * 1e-3)
+    gs.close()
 
     # ---- e2e: host buffers through ca_step_host (H2D actions, D2H obs/reward/done/game_over every step)
-    for e in envs:
-        e.close()
-    del envs
-    torch.cuda.empty_cache()
     Rh = 3
+    T = 12
     henvs = []
     for init, nag in sets[:Rh]:
         h = HostVecEnv(_abi.default_config(W, A, auto_reset=1, device=local_rank))
@@ -312,8 +492,8 @@ def run_ours(args):
         h.reset()
         henvs.append(h)
     host_actions = rng.integers(0, 11, (T, W, A)).astype(np.int32)
-    Ke = min(K, 400)
-    for k in range(3):
+    Ke = max(min(K, 400), 120)                   # e2e is timed over at least 120 steps whatever --steps is
+    for k in range(6):
         henvs[k % Rh].step(host_actions[k % T])
     barrier()
     # (a) strictly synchronous: one ca_step_host (= VecEnv.step) at a time, reported as e2e.sync_value
@@ -343,12 +523,27 @@ def run_ours(args):
     e2e_s = time.perf_counter() - t0
     barrier()
     e2e_s = max_over_ranks(e2e_s)
-    clocks = sampler.stop()
     e2e_value = world_size * Ke * live_agents(W) / e2e_s
     h2d, d2h = henvs[0].h2d_bytes_per_step, henvs[0].d2h_bytes_per_step
-    gpu_launches += Ke + Ks + 3
     for h in henvs:
         h.close()
+    torch.cuda.empty_cache()
+
+    # ---- extra workloads (sub-records; every rank takes part so that N > 1 numbers are whole-job numbers)
+    extras = {}
+    if not args.no_extras and WORKLOAD_NAME == "phase1":
+        def guarded(key, fn):
+            try:
+                extras[key] = fn()
+            except Exception as e:   # an extra record must never take the headline down
+                extras[key] = {"error": repr(e)}
+            barrier()
+        guarded("phase2_env_step", lambda: env_workload_record("phase2", rank, local_rank, 240, barrier, max_over_ranks, world_size))
+        guarded("ragged_env_step", lambda: env_workload_record("ragged", rank, local_rank, 240, barrier, max_over_ranks, world_size))
+        guarded("rollout_phase2_all_present", lambda: rollout_record("TrainPhase2", 16384, 96, True, local_rank, max_over_ranks, world_size))
+        guarded("rollout_phase2_training_mix", lambda: rollout_record("TrainPhase2", 16384, 96, False, local_rank, max_over_ranks, world_size))
+        guarded("train_loop", lambda: train_loop_record(args.train_seconds, 65536, local_rank, world_size))
+    clocks = sampler.stop()
 
     if rank == 0:
         peak, peak_src = measured_peak()
@@ -359,9 +554,12 @@ def run_ours(args):
             "warmup": WU, "ms_per_step": dev_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": WORKLOAD, "worlds_per_gpu": W, "agents_per_world": A, "others_observed": OTHERS,
-                       "obs_len": _abi.obs_len(OTHERS), "launch": "CUDA graph of %d steps replayed" % G,
+                       "obs_len": _abi.obs_len(OTHERS),
+                       "launch": "every timed step replayed from CUDA graphs (%d x %d steps + %d-step tail graph); "
+                                 "%d eager launches before the timed region" % (K // G, G, K % G, eager_launches),
                        "l2": "inputs larger than L2: steps rotate over %d independent world sets (%.0f MB total per GPU)"
-                             % (R, R * bytes_per_set / 1e6)},
+                             % (R, R * bytes_per_set / 1e6),
+                       "extra_workloads": extras},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "agent-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps": Ke,
@@ -369,12 +567,13 @@ def run_ours(args):
                     "api": "ca_step_host_async/_wait = VecEnv.step_async/step_wait over %d independent host envs, pinned host buffers" % Rh},
             "gpu_launches": gpu_launches,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": ncu_traffic_per_launch() if WORKLOAD == WORKLOADS["phase1"][3] else None, "peak_source": peak_src,
+                         "traffic": ncu_traffic_per_launch(WORKLOAD_NAME), "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": ALG_BYTES_PER_AGENT_STEP * live_agents(W),
-                         "kernel": "ca::ca_step_kernel<%d, %d, false>" % (A, MINBLOCKS), "launch_ms": launch_ms},
+                         "kernel": step_kernel_name(), "launch_ms": launch_ms},
         }
         if world_size == 1 and not args.no_cpu_baseline:
-            line["cpu_baseline"] = cpu_baseline_run(args.cpu_seconds, 16384)
+            line["cpu_baseline"] = cpu_baseline_run(args.cpu_seconds)
+            line["cpu_baseline_reference"] = cpu_reference_run(args.cpu_seconds)
         print(json.dumps(line), flush=True)
     if distributed:
         dist.barrier()
@@ -387,10 +586,12 @@ def main():
     ap.add_argument("--steps", type=int, default=2400)
     ap.add_argument("--warmup", type=int, default=48)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--cpu-seconds", type=float, default=10.0, help="wall time of the cpu_baseline sample")
+    ap.add_argument("--cpu-seconds", type=float, default=10.0, help="wall time of each cpu_baseline sample")
+    ap.add_argument("--train-seconds", type=float, default=6.0, help="wall time of the train_loop extra workload")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip config.extra_workloads")
     ap.add_argument("--workload", default="phase1", choices=sorted(WORKLOADS),
-                    help="phase1 = BASELINE configs[1] (the recorded bench line); phase2 / ragged = extra lines")
+                    help="phase1 = BASELINE configs[1] (the recorded bench line); phase2 / ragged = standalone extra lines")
     args = ap.parse_args()
     select_workload(args.workload)
     if args.impl == "reference":

@@ -215,6 +215,11 @@ int ca_reset_host(ca_env* env, const uint8_t* world_mask, float* obs, int32_t* s
  * copies synchronise). */
 int ca_get_state(ca_env* env, double* out, int on_device, void* stream);
 
+/* Time step used by the steps that follow (stream-ordered with them: the value is read when a step is launched).
+ * Replaces the per-call `dt` argument of CollisionAvoidanceEnv.step(actions, dt=None)
+ * (GCA/envs/collision_avoidance_env.py:131-138; Agent.take_action(action, dt), GCA/envs/agent.py:190).  dt must be > 0. */
+int ca_set_dt(ca_env* env, double dt);
+
 /* Number of kernels this handle has launched since creation (bench.py's gpu_launches). */
 int ca_launch_count(const ca_env* env, int64_t* out);
 

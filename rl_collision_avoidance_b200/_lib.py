@@ -26,7 +26,7 @@ NVCC_FLAGS = [
 # every symbol include/ca_step.h declares
 EXPORTS = [
     "ca_default_config", "ca_create", "ca_destroy", "ca_set_world_state", "ca_set_reset_state", "ca_reset", "ca_step", "ca_step_host", "ca_step_host_async", "ca_step_host_wait",
-    "ca_reset_host", "ca_get_state", "ca_launch_count", "ca_host_alloc", "ca_host_free", "ca_nstep_returns",
+    "ca_reset_host", "ca_get_state", "ca_set_dt", "ca_launch_count", "ca_host_alloc", "ca_host_free", "ca_nstep_returns",
     "ca_ga3c_record", "ca_ga3c_episode_stats", "ca_default_scenario_config", "ca_generate_scenarios", "ca_lstm_step", "ca_lstm_cell_forward", "ca_lstm_cell_backward",
     "ca_predictor_pack", "ca_predict", "ca_predict_plan", "ca_predict_rows",
     "ca_strerror", "ca_last_error", "ca_abi_version",
@@ -103,6 +103,7 @@ def lib():
     L.ca_step_host_wait.argtypes = [vp]
     L.ca_reset_host.argtypes = [vp, vp, vp, vp]
     L.ca_get_state.argtypes = [vp, vp, C.c_int, vp]
+    L.ca_set_dt.argtypes = [vp, C.c_double]
     L.ca_launch_count.argtypes = [vp, C.POINTER(i64)]
     L.ca_host_alloc.argtypes = [C.POINTER(vp), C.c_uint64]
     L.ca_host_free.argtypes = [vp]

@@ -646,6 +646,22 @@ __global__ void __launch_bounds__(256) plan_scatter_kernel(const float* __restri
 // ---- C-ABI ------------------------------------------------------------------------------------------------------------
 int ca_fail_external(int code, const char* msg);  // ca_step.cu: records the message for ca_last_error
 
+// Makes `device` current for the duration of a call and restores the caller's device afterwards (same contract as the
+// entry points of ca_step.cu).
+namespace {
+struct PredDeviceGuard {
+  int prev = -1, target = -1;
+  bool ok = true;
+  explicit PredDeviceGuard(int dev) : target(dev) {
+    if (cudaGetDevice(&prev) != cudaSuccess) { ok = false; return; }
+    if (prev != dev && cudaSetDevice(dev) != cudaSuccess) ok = false;
+  }
+  ~PredDeviceGuard() {
+    if (ok && prev >= 0 && prev != target) cudaSetDevice(prev);
+  }
+};
+}  // namespace
+
 extern "C" {
 
 int ca_predictor_pack(const ca_predictor_params* w, void* blob, int device, void* stream) {
@@ -653,7 +669,8 @@ int ca_predictor_pack(const ca_predictor_params* w, void* blob, int device, void
   const float* const* ptrs = reinterpret_cast<const float* const*>(w);
   for (int i = 0; i < 14; ++i)
     if (!ptrs[i]) return ca_fail_external(CA_ERR_INVALID_ARG, "ca_predictor_pack: NULL parameter pointer");
-  if (cudaSetDevice(device) != cudaSuccess) return ca_fail_external(CA_ERR_CUDA, "cudaSetDevice failed");
+  PredDeviceGuard guard(device);
+  if (!guard.ok) return ca_fail_external(CA_ERR_CUDA, "cudaSetDevice failed");
   cap::PackParams q;
   q.k_lstm = w->lstm_kernel; q.b_lstm = w->lstm_bias; q.k_l1 = w->layer1_kernel; q.b_l1 = w->layer1_bias;
   q.k_l2 = w->layer2_kernel; q.b_l2 = w->layer2_bias; q.k_fc1 = w->fc1_kernel; q.b_fc1 = w->fc1_bias;
@@ -675,15 +692,15 @@ static int predict_launch(const float* obs, int32_t obs_stride, int32_t batch, i
     return ca_fail_external(CA_ERR_INVALID_ARG, "ca_predict_rows: row_index and n_rows go together");
   if (num_others > cap::kMaxOthers)
     return ca_fail_external(CA_ERR_UNSUPPORTED, "ca_predict: more than 22 observed other agents");
-  if (cudaSetDevice(device) != cudaSuccess) return ca_fail_external(CA_ERR_CUDA, "cudaSetDevice failed");
-  static int sms[64] = {0};
-  if (device < 64 && sms[device] == 0) {
-    if (cudaFuncSetAttribute(cap::predict_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, cap::kSmTotal) != cudaSuccess)
-      return ca_fail_external(CA_ERR_CUDA, "ca_predict: kernel image not usable on this device (built for sm_100a)");
-    cudaFuncSetAttribute(cap::predict_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100);  // two CTAs per SM
-    cudaDeviceGetAttribute(&sms[device], cudaDevAttrMultiProcessorCount, device);
-  }
-  const int n_sm = device < 64 ? sms[device] : 148;
+  PredDeviceGuard guard(device);
+  if (!guard.ok) return ca_fail_external(CA_ERR_CUDA, "cudaSetDevice failed");
+  // function attributes are per device and idempotent: set on every call (two cheap driver calls) instead of keeping a
+  // process-wide table that concurrent callers would race on
+  if (cudaFuncSetAttribute(cap::predict_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, cap::kSmTotal) != cudaSuccess)
+    return ca_fail_external(CA_ERR_CUDA, "ca_predict: kernel image not usable on this device (built for sm_100a)");
+  cudaFuncSetAttribute(cap::predict_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100);  // two CTAs per SM
+  int n_sm = 0;
+  if (cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, device) != cudaSuccess || n_sm < 1) n_sm = 148;
   cap::Params q;
   q.obs = obs; q.stride = obs_stride; q.B = batch; q.M = num_others;
   q.blob = static_cast<const unsigned char*>(blob);
@@ -711,7 +728,8 @@ int ca_predict_plan(const float* obs, int32_t obs_stride, int32_t batch, int32_t
     return ca_fail_external(CA_ERR_INVALID_ARG, "ca_predict_plan: bad argument");
   if (num_others > cap::kMaxOthers)
     return ca_fail_external(CA_ERR_UNSUPPORTED, "ca_predict_plan: more than 22 observed other agents");
-  if (cudaSetDevice(device) != cudaSuccess) return ca_fail_external(CA_ERR_CUDA, "cudaSetDevice failed");
+  PredDeviceGuard guard(device);
+  if (!guard.ok) return ca_fail_external(CA_ERR_CUDA, "cudaSetDevice failed");
   cudaStream_t st = (cudaStream_t)stream;
   if (cudaMemsetAsync(counters, 0, CA_PREDICT_PLAN_COUNTERS * sizeof(int32_t), st) != cudaSuccess)
     return ca_fail_external(CA_ERR_CUDA, "ca_predict_plan: memset failed");

@@ -57,6 +57,7 @@ int ca_fail_external(int code, const char* msg) { return fail(code, "%s", msg); 
 
 struct ca_env {
   ca_config cfg;
+  double step_dt = 0.0;        // dt of the next steps (ca_set_dt); cfg.dt = Config.DT is what reset's time budget uses
   int W = 0, A = 0, M = 0, L = 0, wpw = 0;
   int grid = 0;
   size_t smem_bytes = 0;
@@ -89,6 +90,9 @@ struct ca_env {
   uint8_t* d_over = nullptr;
   uint8_t* d_mask = nullptr;
   int32_t* d_sidx = nullptr;
+  // staging for the host-side ca_set_world_state / ca_set_reset_state / ca_get_state (lazily allocated, owned by the handle)
+  double* d_boundary = nullptr;   // max(W*A*CA_INIT_STRIDE, W*A*CA_STATE_STRIDE) doubles
+  int32_t* d_boundary_nag = nullptr;
 };
 
 namespace {
@@ -160,7 +164,7 @@ ca::Params make_params(const ca_env* e) {
   p.W = e->W; p.A = e->A; p.M = e->M; p.L = e->L; p.wpw = e->wpw;
   p.sort_method = c.sort_method; p.over_mode = c.game_over_mode; p.auto_reset = c.auto_reset;
   p.tile_floats = e->tile_floats;
-  p.dt = c.dt;
+  p.dt = e->step_dt;
   p.thr_sq = std::pow(c.near_goal_threshold, 2.0);  // near_goal_threshold**2 as Python evaluates it (agent.py:150)
   p.close_range = c.getting_close_range;
   p.r_goal = c.reward_at_goal; p.r_coll = c.reward_collision_with_agent; p.r_step = c.reward_time_step;
@@ -313,6 +317,20 @@ int ensure_staging(ca_env* e) {
   return CA_OK;
 }
 
+int ensure_boundary(ca_env* e) {
+  if (e->d_boundary) return CA_OK;
+  const size_t n = (size_t)e->W * e->A;
+  const size_t stride = CA_INIT_STRIDE > CA_STATE_STRIDE ? CA_INIT_STRIDE : CA_STATE_STRIDE;
+  CA_CUDA(cudaMalloc(&e->d_boundary, n * stride * sizeof(double)));
+  if (cudaMalloc(&e->d_boundary_nag, (size_t)e->W * sizeof(int32_t)) != cudaSuccess) {
+    cudaFree(e->d_boundary);
+    e->d_boundary = nullptr;
+    cudaGetLastError();
+    return fail(CA_ERR_ALLOC, "cudaMalloc of the boundary staging failed");
+  }
+  return CA_OK;
+}
+
 }  // namespace
 
 extern "C" {
@@ -386,6 +404,7 @@ int ca_create(const ca_config* cfg, ca_env** out) {
   ca_env* e = new (std::nothrow) ca_env();
   if (!e) return fail(CA_ERR_ALLOC, "out of host memory");
   e->cfg = *cfg;
+  e->step_dt = cfg->dt;
   e->W = cfg->num_worlds; e->A = cfg->max_agents; e->M = cfg->max_others_observed;
   e->L = CA_OBS_LEN(e->M);
   e->wpw = ca::worlds_per_chunk(e->A);
@@ -477,6 +496,7 @@ int ca_destroy(ca_env* e) {
   cudaFree(e->slab); cudaFree(e->consumed); cudaFree(e->ticket);
   cudaFree(e->d_actions); cudaFree(e->d_cont); cudaFree(e->d_obs); cudaFree(e->d_reward);
   cudaFree(e->d_done); cudaFree(e->d_over); cudaFree(e->d_mask); cudaFree(e->d_sidx);
+  cudaFree(e->d_boundary); cudaFree(e->d_boundary_nag);
   if (e->hstream) cudaStreamDestroy(e->hstream);
   delete e;
   return CA_OK;
@@ -490,18 +510,16 @@ static int set_state_impl(ca_env* e, const double* init, const int32_t* num_agen
   const size_t n = (size_t)e->W * e->A;
   const double* d_init = init;
   const int32_t* d_nag = num_agents;
-  double* tmp_init = nullptr;
-  int32_t* tmp_nag = nullptr;
   if (!on_device) {
     for (int w = 0; w < e->W; ++w)
       if (num_agents[w] < 1 || num_agents[w] > e->A)
         return fail(CA_ERR_INVALID_ARG, "num_agents[%d] = %d outside 1..%d", w, num_agents[w], e->A);
-    CA_CUDA(cudaMalloc(&tmp_init, n * CA_INIT_STRIDE * sizeof(double)));
-    CA_CUDA(cudaMalloc(&tmp_nag, (size_t)e->W * sizeof(int32_t)));
-    CA_CUDA(cudaMemcpyAsync(tmp_init, init, n * CA_INIT_STRIDE * sizeof(double), cudaMemcpyHostToDevice, st));
-    CA_CUDA(cudaMemcpyAsync(tmp_nag, num_agents, (size_t)e->W * sizeof(int32_t), cudaMemcpyHostToDevice, st));
-    d_init = tmp_init;
-    d_nag = tmp_nag;
+    const int rc = ensure_boundary(e);   // handle-owned staging: nothing to free on the error paths below
+    if (rc != CA_OK) return rc;
+    CA_CUDA(cudaMemcpyAsync(e->d_boundary, init, n * CA_INIT_STRIDE * sizeof(double), cudaMemcpyHostToDevice, st));
+    CA_CUDA(cudaMemcpyAsync(e->d_boundary_nag, num_agents, (size_t)e->W * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    d_init = e->d_boundary;
+    d_nag = e->d_boundary_nag;
   }
   const int threads = 256;
   const int blocks = (int)((n + threads - 1) / threads);
@@ -509,11 +527,7 @@ static int set_state_impl(ca_env* e, const double* init, const int32_t* num_agen
                                                  e->cfg.near_goal_threshold, e->cfg.dt, snapshot_only);
   CA_CUDA(cudaPeekAtLastError());
   e->launches += 1;
-  if (!on_device) {
-    CA_CUDA(cudaStreamSynchronize(st));
-    cudaFree(tmp_init);
-    cudaFree(tmp_nag);
-  }
+  if (!on_device) CA_CUDA(cudaStreamSynchronize(st));   // the staging may be reused by the next call
   if (!snapshot_only) e->initialised = true;
   return CA_OK;
 }
@@ -617,7 +631,11 @@ int ca_get_state(ca_env* e, double* out, int on_device, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   const size_t n = (size_t)e->W * e->A;
   double* d_out = out;
-  if (!on_device) CA_CUDA(cudaMalloc(&d_out, n * CA_STATE_STRIDE * sizeof(double)));
+  if (!on_device) {
+    const int rc = ensure_boundary(e);
+    if (rc != CA_OK) return rc;
+    d_out = e->d_boundary;
+  }
   const int threads = 256;
   pack_state_kernel<<<(int)((n + threads - 1) / threads), threads, 0, st>>>(e->s, d_out, e->W, e->A);
   CA_CUDA(cudaPeekAtLastError());
@@ -625,8 +643,14 @@ int ca_get_state(ca_env* e, double* out, int on_device, void* stream) {
   if (!on_device) {
     CA_CUDA(cudaMemcpyAsync(out, d_out, n * CA_STATE_STRIDE * sizeof(double), cudaMemcpyDeviceToHost, st));
     CA_CUDA(cudaStreamSynchronize(st));
-    cudaFree(d_out);
   }
+  return CA_OK;
+}
+
+int ca_set_dt(ca_env* e, double dt) {
+  if (!e) return fail(CA_ERR_INVALID_ARG, "NULL argument");
+  if (!(dt > 0) || !std::isfinite(dt)) return fail(CA_ERR_INVALID_ARG, "dt must be > 0");
+  e->step_dt = dt;   // make_params() copies it into the next launch's parameters; Config.DT (reset time budget) stays
   return CA_OK;
 }
 

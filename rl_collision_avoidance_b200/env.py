@@ -197,6 +197,7 @@ class CollisionAvoidanceEnv(object):
                                                        info['bounds'][1] * np.ones(info['size']), dtype=info['dtype'])
         self._ca_cfg = _config.to_ca_config(cfg, 1, device=device)
         self._env = HostVecEnv(self._ca_cfg, want_sorted_idx=True)
+        self._dt_in_use = self.dt_nominal
         self.agents = None
         self.default_agents = None
         self.prev_episode_agents = None
@@ -222,11 +223,15 @@ class CollisionAvoidanceEnv(object):
         self.default_agents = agents
 
     def set_testcase(self, test_case_fn_str, test_case_args):
-        if test_case_fn_str != "get_testcase_random":
-            raise NotImplementedError("only get_testcase_random is available on the GPU path; build Agents and call "
-                                      "set_agents() for anything else")
+        """GCA/envs/collision_avoidance_env.py:294-298: the generator reset() calls when no agents were injected.
+        Available: get_testcase_random (test_cases.py:95-118) and get_testcase_two_agents (:77-84); the preset suites
+        (:176-512) read pickled test sets and use CADRL / RVO policies, which are out of scope — build Agents and call
+        set_agents() for those."""
+        if test_case_fn_str not in ("get_testcase_random", "get_testcase_two_agents"):
+            raise NotImplementedError("test case generator %r is not available on the GPU path; build Agents and call "
+                                      "set_agents() instead" % (test_case_fn_str,))
         self.test_case_fn_str = test_case_fn_str
-        self.test_case_args = test_case_args
+        self.test_case_args = dict(test_case_args or {})
 
     def set_static_map(self, map_filename):
         self.static_map_filename = map_filename
@@ -246,7 +251,7 @@ class CollisionAvoidanceEnv(object):
             self.episode_number += 1
         self.episode_step_number = 0
         if self.default_agents is None:
-            self.agents = self._random_agents()
+            self.agents = self._two_agents() if self.test_case_fn_str == "get_testcase_two_agents" else self._random_agents()
         else:
             self.agents = self.default_agents
         if len(self.agents) > cfg.MAX_NUM_AGENTS_IN_ENVIRONMENT:
@@ -266,9 +271,10 @@ class CollisionAvoidanceEnv(object):
     def step(self, actions, dt=None):
         """CollisionAvoidanceEnv.step, :131-194.  `actions`: dict agent index -> discrete action (learning_ga3c)
         or [speed_frac, heading_frac] (learning); agents with internal policies need no entry."""
-        if dt is not None and dt != self.dt_nominal:
-            raise NotImplementedError("a per-call dt different from Config.DT is not supported on the GPU path")
-        dt = self.dt_nominal
+        dt = self.dt_nominal if dt is None else float(dt)   # :137-138
+        if dt != self._dt_in_use:
+            self._env.handle.set_dt(dt)
+            self._dt_in_use = dt
         self.episode_step_number += 1
         A = self._env.A
         act = np.zeros((1, A), dtype=np.int32)
@@ -320,6 +326,13 @@ class CollisionAvoidanceEnv(object):
         st = self._env.get_state()[0]
         for i, a in enumerate(self.agents):
             a._read_back(st[i], self._env.obs[0, i], False if moved is None else moved[i], dt)
+
+    def _two_agents(self):
+        """get_testcase_two_agents (GCA/envs/test_cases.py:77-84): two agents swapping corners of a 6 m square."""
+        policies = self.test_case_args.get('policies', ['learning', 'learning_ga3c'])
+        g = 3
+        return [Agent(-g, -g, g, g, 0.5, 1.0, 0.0, policy_dict[policies[0]], UnicycleDynamics, [OtherAgentsStatesSensor], 0),
+                Agent(g, g, -g, -g, 0.5, 1.0, np.pi, policy_dict[policies[1]], UnicycleDynamics, [OtherAgentsStatesSensor], 1)]
 
     def _random_agents(self):
         """get_testcase_random (GCA/envs/test_cases.py:95-118) for one world, via scenarios.random_worlds."""

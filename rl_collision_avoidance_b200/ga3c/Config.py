@@ -91,8 +91,19 @@ class Train(EnvConfig):
 
         # ---- GPU-only knobs
         s.GPU_NUM_WORLDS = int(os.environ.get('GA3C_GPU_NUM_WORLDS', 4096))   # worlds stepped per launch on each GPU
-        # rows per optimiser step (>= TRAINING_MIN_BATCH_SIZE); 0 = auto: about one step per env step (max(8192, worlds * agents))
+        # rows per optimiser step (>= TRAINING_MIN_BATCH_SIZE); 0 = auto = 8192 rows, the batch the committed learning curve
+        # (profiles/r02_learning_curve.json) was validated with
         s.GPU_TRAIN_BATCH = int(os.environ.get('GA3C_GPU_TRAIN_BATCH', 0))
+        # The reference's trainer takes one Adam step per ~100-200 rows (ThreadTrainer.py:44) with SUM losses, i.e. about
+        # a million updates over a TrainPhase1 run.  A vectorised trainer that steps once per GPU_TRAIN_BATCH rows takes
+        # GPU_TRAIN_BATCH / GPU_REF_BATCH times fewer steps; Adam normalises the gradient scale, so each step moves the
+        # weights by ~lr whatever the batch — the learning rate therefore has to grow with the batch to cover the same
+        # distance in weight space.  GPU_LR_SCALE: 'linear' (lr * B / GPU_REF_BATCH, the update budget of the reference
+        # cadence), 'sqrt', 'none', or a number (explicit multiplier); capped by GPU_LR_MAX.  DESIGN.md §6 has the
+        # learning curves this default was chosen from.
+        s.GPU_REF_BATCH = 128
+        s.GPU_LR_SCALE = os.environ.get('GA3C_GPU_LR_SCALE', 'sqrt')
+        s.GPU_LR_MAX = float(os.environ.get('GA3C_GPU_LR_MAX', 3e-3))
         s.GPU_PRINT_EVERY_S = 2.0
         # trainer matmuls on the tensor cores in TF32 (10-bit significand, fp32 accumulation); off = fp32 like the reference
         s.GPU_TRAIN_TF32 = int(os.environ.get('GA3C_GPU_TRAIN_TF32', 0))

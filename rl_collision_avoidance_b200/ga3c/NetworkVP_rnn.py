@@ -106,6 +106,7 @@ class PolicyValueNet(torch.nn.Module):
         with torch.no_grad():
             for name, value in variables.items():
                 self.w(name).copy_(torch.as_tensor(value, dtype=torch.float32))
+        self.weights_version = getattr(self, "weights_version", 0) + 1   # invalidates the packed predictor image
 
     def features(self, x):
         H = self.HIDDEN
@@ -272,7 +273,7 @@ class NetworkVP_rnn(object):
     def _packed_blob(self):
         import ctypes as C
         from .._lib import check, lib
-        version = (self.global_step, getattr(self, "_load_count", 0))
+        version = (self.global_step, getattr(self, "_load_count", 0), getattr(self.net, "weights_version", 0))
         if getattr(self, "_packed_version", None) == version:
             return self._blob
         net = self.net
@@ -332,6 +333,14 @@ class NetworkVP_rnn(object):
                                ptr(self._pred_error), obs.device.index or 0, stream), "ca_predict")
         return p, v, actions
 
+    def check_predictor_error(self):
+        """Raises if the fused predictor flagged a tile (an mbarrier wait that timed out leaves garbage actions / values);
+        clears the flag.  One 4-byte D2H read: call it where the loop synchronises anyway."""
+        err = getattr(self, "_pred_error", None)
+        if err is not None and int(err.item()) != 0:
+            err.zero_()
+            raise RuntimeError("fused predictor reported a timed-out tile (device error flag set)")
+
     def predict_p_and_v(self, x):
         p, v = self.predict_p_and_v_device(self._as_input(x))
         return p.cpu().numpy(), v.cpu().numpy()
@@ -366,18 +375,39 @@ class NetworkVP_rnn(object):
         x = self._as_input(x)
         y_r = self._as_input(y_r)
         a = torch.as_tensor(a, device=self.device)
+        costs = self.backward(x, y_r, a)
+        self.apply_gradients()
+        return costs
+
+    def backward(self, x, y_r, a):
+        """Sum-loss gradients of one batch of rows into p.grad for EVERY parameter (an empty batch gives zeros, so that
+        ranks with nothing to contribute still take part in the gradient all-reduce)."""
+        params = list(self.net.parameters())
+        if x.shape[0] == 0:
+            for p in params:
+                p.grad = torch.zeros_like(p)
+            zero = torch.zeros((), device=self.device)
+            self.last_costs = {k: zero for k in ("cost_all", "cost_p", "cost_v", "cost_p_advant_agg", "cost_p_entrop_agg")}
+            return self.last_costs
         costs = self.losses(x, y_r, a)
-        for p in self.net.parameters():
+        for p in params:
             p.grad = None
         costs["cost_all"].backward()
+        for p in params:
+            if p.grad is None:
+                p.grad = torch.zeros_like(p)
+        self.last_costs = costs
+        return costs
+
+    def apply_gradients(self):
+        """tf.clip_by_average_norm (if configured) + the TF-Adam step on whatever is in p.grad (NetworkVPCore.py:100-123);
+        the distributed trainer calls it after the gradient all-reduce, so both paths train the same way."""
         if self.cfg.USE_GRAD_CLIP:
-            for p in self.net.parameters():  # tf.clip_by_average_norm
+            for p in self.net.parameters():
                 avg_norm = p.grad.norm() / p.grad.numel()
                 p.grad.mul_(torch.clamp(self.cfg.GRAD_CLIP_NORM / (avg_norm + 1e-12), max=1.0))
         self.opt.step(self.learning_rate)
         self.global_step += 1
-        self.last_costs = costs
-        return costs
 
     def get_global_step(self):
         return self.global_step

@@ -127,6 +127,26 @@ class Server(object):
         self.rollout.attach_scenario_generator(self._scenario_cfg, self._scenario_seed)   # refill after every step
         self._pending = []
         self._pending_rows = 0
+        self.history = []   # (seconds, episodes, rolling score, optimiser steps, frames) at every stats refresh
+
+    def train_batch_rows(self):
+        """Rows per optimiser step."""
+        cfg = self.cfg
+        return max(cfg.GPU_TRAIN_BATCH if cfg.GPU_TRAIN_BATCH > 0 else 8192, cfg.TRAINING_MIN_BATCH_SIZE + 1)
+
+    def lr_multiplier(self):
+        """Learning-rate factor that compensates for taking one optimiser step per train_batch_rows() * world_size rows
+        instead of one per ~GPU_REF_BATCH rows (Config.GPU_LR_SCALE)."""
+        cfg = self.cfg
+        ratio = max(1.0, self.train_batch_rows() * self.world_size / float(cfg.GPU_REF_BATCH))
+        mode = str(cfg.GPU_LR_SCALE)
+        if mode == 'none':
+            return 1.0
+        if mode == 'linear':
+            return ratio
+        if mode == 'sqrt':
+            return ratio ** 0.5
+        return float(mode)
 
     def make_model(self):
         cfg = self.cfg
@@ -161,14 +181,9 @@ class Server(object):
     def _train_distributed(self, x_, r_, a_):
         """Sum-loss gradients are summed over ranks (== one trainer seeing the concatenation of all ranks' rows)."""
         m = self.model
-        costs = m.losses(m._as_input(x_), m._as_input(r_), self.torch.as_tensor(a_, device=m.device))
-        for p in m.net.parameters():
-            p.grad = None
-        costs["cost_all"].backward()
-        allreduce_gradients(list(m.net.parameters()))
-        m.opt.step(m.learning_rate)
-        m.global_step += 1
-        m.last_costs = costs
+        costs = m.backward(m._as_input(x_), m._as_input(r_), self.torch.as_tensor(a_, device=m.device))
+        allreduce_gradients(list(m.net.parameters()))   # fixed parameter list, zeros from ranks without rows
+        m.apply_gradients()                             # clip (if configured) + Adam, as on the single-GPU path
         return costs
 
     def save_model(self):
@@ -177,8 +192,7 @@ class Server(object):
 
     def _train_pending(self, force=False):
         cfg = self.cfg
-        auto = max(8192, self.num_worlds * cfg.MAX_NUM_AGENTS_IN_ENVIRONMENT)
-        batch = max(cfg.GPU_TRAIN_BATCH if cfg.GPU_TRAIN_BATCH > 0 else auto, cfg.TRAINING_MIN_BATCH_SIZE + 1)
+        batch = self.train_batch_rows()
         torch = self.torch
         if self.dist:
             return self._train_pending_distributed(batch, force)
@@ -216,17 +230,19 @@ class Server(object):
                 self.train_model(xs, rs, as_, 0)
         self._pending, self._pending_rows = [], 0
 
-    def main(self, max_steps=None, max_seconds=None, quiet=False):
-        """Runs until Config.EPISODES (or max_steps / max_seconds, for tests and benchmarks)."""
+    def main(self, max_steps=None, max_seconds=None, quiet=False, until_score=None):
+        """Runs until Config.EPISODES (or max_steps / max_seconds / a rolling score of until_score, for tests and
+        benchmarks)."""
         cfg = self.cfg
         lr_mult = (cfg.LEARNING_RATE_RL_END - cfg.LEARNING_RATE_RL_START) / cfg.ANNEALING_EPISODE_COUNT
         beta_mult = (cfg.BETA_END - cfg.BETA_START) / cfg.ANNEALING_EPISODE_COUNT
         t0 = last_print = time.time()
         steps = 0
         refresh_every = max(8, cfg.TIME_MAX)
+        lr_scale = self.lr_multiplier()
         while self.stats.episode_count < cfg.EPISODES:
             step = min(self.stats.episode_count, cfg.ANNEALING_EPISODE_COUNT - 1)   # Server.main :143-148
-            self.model.learning_rate = cfg.LEARNING_RATE_RL_START + lr_mult * step
+            self.model.learning_rate = min((cfg.LEARNING_RATE_RL_START + lr_mult * step) * lr_scale, cfg.GPU_LR_MAX)
             self.model.beta = cfg.BETA_START + beta_mult * step
             self.rollout.step()
             steps += 1
@@ -242,6 +258,9 @@ class Server(object):
                     self.dist.all_reduce(t)
                     s = {"episodes": int(t[0].item()), "score_sum": float(t[1].item()), "frames": int(t[2].item())}
                 self.stats.add(s["episodes"], s["score_sum"], s["frames"])
+                self.model.check_predictor_error()
+                self.history.append((time.time() - t0, self.stats.episode_count, self.stats.roll_reward_log,
+                                     self.training_step, self.stats.total_frame_count))
                 if cfg.SAVE_MODELS and self.stats.should_save_model > 0:
                     self.save_model()
                     self.stats.should_save_model = 0
@@ -252,8 +271,10 @@ class Server(object):
                 last_print = now
             if max_steps is not None and steps >= max_steps:
                 break
-            if max_seconds is not None and steps % refresh_every == 0:
-                stop = now - t0 >= max_seconds
+            if (max_seconds is not None or until_score is not None) and steps % refresh_every == 0:
+                stop = max_seconds is not None and now - t0 >= max_seconds
+                if until_score is not None and self.stats.window and self.stats.roll_reward_log >= until_score:
+                    stop = True
                 if self.dist:  # all ranks must leave the loop in the same iteration
                     flag = self.torch.tensor([1.0 if stop else 0.0], device="cuda")
                     self.dist.all_reduce(flag, op=self.dist.ReduceOp.MAX)

@@ -52,8 +52,12 @@ def broadcast_weights(parameters, src=0, group=None):
 
 
 def allreduce_gradients(parameters, group=None):
-    """Sum gradients over ranks in one flat collective."""
-    params = [p for p in parameters if p.grad is not None]
+    """Sum gradients over ranks in one flat collective.  The buffer covers EVERY parameter (a missing gradient counts as
+    zeros), so its length is the same on all ranks whatever rows each of them had."""
+    params = list(parameters)
+    for p in params:
+        if p.grad is None:
+            p.grad = torch.zeros_like(p)
     flat = torch.cat([p.grad.reshape(-1) for p in params])
     dist.all_reduce(flat, group=group)
     off = 0

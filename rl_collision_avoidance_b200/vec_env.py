@@ -56,6 +56,10 @@ class CaHandle(object):
         check(lib().ca_launch_count(self._h, C.byref(out)), "ca_launch_count")
         return out.value
 
+    def set_dt(self, dt):
+        """Time step of the steps that follow (the per-call dt of CollisionAvoidanceEnv.step)."""
+        check(lib().ca_set_dt(self._h, float(dt)), "ca_set_dt")
+
     def set_world_state(self, init_ptr, nag_ptr, on_device, stream=None, snapshot_only=False):
         if snapshot_only:
             check(lib().ca_set_reset_state(self._h, init_ptr, nag_ptr, int(on_device), stream), "ca_set_reset_state")
