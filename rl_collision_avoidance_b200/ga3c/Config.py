@@ -105,6 +105,8 @@ class Train(EnvConfig):
         s.GPU_LR_SCALE = os.environ.get('GA3C_GPU_LR_SCALE', 'sqrt')
         s.GPU_LR_MAX = float(os.environ.get('GA3C_GPU_LR_MAX', 3e-3))
         s.GPU_PRINT_EVERY_S = 2.0
+        # optimiser steps on exactly GPU_TRAIN_BATCH rows replayed from CUDA graphs (NetworkVP_rnn.GraphedTrainStep)
+        s.GPU_TRAIN_GRAPH = int(os.environ.get('GA3C_GPU_TRAIN_GRAPH', 1))
         # trainer matmuls on the tensor cores in TF32 (10-bit significand, fp32 accumulation); off = fp32 like the reference
         s.GPU_TRAIN_TF32 = int(os.environ.get('GA3C_GPU_TRAIN_TF32', 0))
 

@@ -152,29 +152,68 @@ class PolicyValueNet(torch.nn.Module):
         return p, v, logits_p
 
 
+def flatten_parameters(params):
+    """Rebinds the parameters (and their .grad) as views into one flat buffer each; returns (flat_param, flat_grad).
+    The optimiser and the gradient all-reduce then work on single tensors, and gradients accumulate in place."""
+    params = list(params)
+    n = sum(p.numel() for p in params)
+    dev = params[0].device
+    flat_param = torch.empty(n, dtype=torch.float32, device=dev)
+    flat_grad = torch.zeros(n, dtype=torch.float32, device=dev)
+    off = 0
+    with torch.no_grad():
+        for p in params:
+            k = p.numel()
+            flat_param[off:off + k].copy_(p.data.reshape(-1))
+            p.data = flat_param[off:off + k].view_as(p)
+            p.grad = flat_grad[off:off + k].view_as(p)
+            off += k
+    return flat_param, flat_grad
+
+
 class TFAdam(object):
     """tf.train.AdamOptimizer update rule (beta1 .9, beta2 .999, eps 1e-8):
-    lr_t = lr * sqrt(1 - b2^t) / (1 - b1^t);  var -= lr_t * m / (sqrt(v) + eps)."""
+    lr_t = lr * sqrt(1 - b2^t) / (1 - b1^t);  var -= lr_t * m / (sqrt(v) + eps).
+    Works on ONE flat parameter / gradient buffer (the parameters are views into it, see NetworkVP_rnn._flatten), so a
+    step is a handful of element-wise kernels; step_device() takes the learning rate as a device scalar and keeps the
+    step count on the device, which makes it capturable in a CUDA graph."""
 
-    def __init__(self, params, beta1=0.9, beta2=0.999, eps=1e-8):
+    def __init__(self, params, flat_param=None, flat_grad=None, beta1=0.9, beta2=0.999, eps=1e-8):
         self.params = [p for p in params]
+        if flat_param is None:
+            flat_param, flat_grad = flatten_parameters(self.params)
+        self.flat_param, self.flat_grad = flat_param, flat_grad
         self.b1, self.b2, self.eps = beta1, beta2, eps
-        self.m = [torch.zeros_like(p) for p in self.params]
-        self.v = [torch.zeros_like(p) for p in self.params]
+        self.flat_m = torch.zeros_like(flat_param)
+        self.flat_v = torch.zeros_like(flat_param)
+        self.m, self.v, off = [], [], 0
+        for p in self.params:   # per-parameter views (checkpoint layout)
+            n = p.numel()
+            self.m.append(self.flat_m[off:off + n].view_as(p))
+            self.v.append(self.flat_v[off:off + n].view_as(p))
+            off += n
         self.t = 0
+        self.t_dev = torch.zeros((), dtype=torch.float64, device=flat_param.device)
 
     @torch.no_grad()
     def step(self, lr):
         self.t += 1
+        self.t_dev.fill_(self.t)
         lr_t = lr * math.sqrt(1.0 - self.b2 ** self.t) / (1.0 - self.b1 ** self.t)
-        grads = [p.grad for p in self.params]
-        torch._foreach_mul_(self.m, self.b1)
-        torch._foreach_add_(self.m, grads, alpha=1.0 - self.b1)
-        torch._foreach_mul_(self.v, self.b2)
-        torch._foreach_addcmul_(self.v, grads, grads, value=1.0 - self.b2)
-        denom = torch._foreach_sqrt(self.v)
-        torch._foreach_add_(denom, self.eps)
-        torch._foreach_addcdiv_(self.params, self.m, denom, value=-lr_t)
+        g = self.flat_grad
+        self.flat_m.mul_(self.b1).add_(g, alpha=1.0 - self.b1)
+        self.flat_v.mul_(self.b2).addcmul_(g, g, value=1.0 - self.b2)
+        self.flat_param.addcdiv_(self.flat_m, self.flat_v.sqrt().add_(self.eps), value=-lr_t)
+
+    @torch.no_grad()
+    def step_device(self, lr_dev):
+        """The same update with lr a 0-dim float64 device tensor and the step count read from / advanced on the device."""
+        self.t_dev.add_(1.0)
+        lr_t = (lr_dev * torch.sqrt(1.0 - torch.pow(self.b2, self.t_dev)) / (1.0 - torch.pow(self.b1, self.t_dev))).to(torch.float32)
+        g = self.flat_grad
+        self.flat_m.mul_(self.b1).add_(g, alpha=1.0 - self.b1)
+        self.flat_v.mul_(self.b2).addcmul_(g, g, value=1.0 - self.b2)
+        self.flat_param.sub_(lr_t * self.flat_m / self.flat_v.sqrt().add_(self.eps))
 
     def state_dict(self):
         return {"m": self.m, "v": self.v, "t": self.t}
@@ -185,6 +224,93 @@ class TFAdam(object):
         for dst, src in zip(self.v, sd["v"]):
             dst.copy_(src)
         self.t = int(sd["t"])
+        self.t_dev.fill_(self.t)
+
+
+class GraphedTrainStep(object):
+    """One optimiser step on a FIXED number of rows — gradient zeroing, forward, sum losses, backward, (clip,) TF-Adam —
+    captured once and replayed as CUDA graphs: a step is then bound by its ~100 small kernels' GPU time instead of their
+    launch overhead (8192 rows: 2.1 ms eager -> a few hundred microseconds).  With `allreduce` given (distributed
+    trainer) the capture is split around the gradient all-reduce: graph A = zero / forward / backward, the collective runs
+    eagerly on the flat gradient buffer, graph B = clip / Adam.  Learning rate and entropy weight are device scalars, so
+    annealing them needs no re-capture."""
+
+    def __init__(self, model, rows, allreduce=None):
+        self.model, self.rows, self.allreduce = model, int(rows), allreduce
+        dev = model.device
+        L1 = model.cfg.NN_INPUT_SIZE
+        self.x = torch.zeros((self.rows, L1), dtype=torch.float32, device=dev)
+        self.r = torch.zeros(self.rows, dtype=torch.float32, device=dev)
+        self.a = torch.zeros(self.rows, dtype=torch.int64, device=dev)
+        self.lr = torch.zeros((), dtype=torch.float64, device=dev)
+        self.beta = torch.zeros((), dtype=torch.float32, device=dev)
+        self._lr_val = self._beta_val = None
+        self.costs = None
+        m = model
+        saved = (m.flat_param.clone(), m.opt.flat_m.clone(), m.opt.flat_v.clone(), m.opt.t)
+        self._set_scalars(m.learning_rate, m.beta)
+        try:   # the .grad views were created on another stream than the capture stream: intended, not a hazard
+            torch.autograd.graph.set_warn_on_accumulate_grad_stream_mismatch(False)
+        except AttributeError:
+            pass
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for _ in range(3):   # warm-up on the side stream (allocator, cuBLAS workspaces, lazy kernel loading)
+                self._backward_body()
+                self._update_body()
+            side.synchronize()
+            self.g_bwd = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.g_bwd, stream=side):
+                self._backward_body()
+                if allreduce is None:
+                    self._update_body()
+            self.g_upd = None
+            if allreduce is not None:
+                self.g_upd = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(self.g_upd, stream=side):
+                    self._update_body()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        with torch.no_grad():   # the warm-up steps must not count
+            m.flat_param.copy_(saved[0]); m.opt.flat_m.copy_(saved[1]); m.opt.flat_v.copy_(saved[2])
+        m.opt.t = saved[3]
+        m.opt.t_dev.fill_(m.opt.t)
+
+    def _set_scalars(self, lr, beta):
+        if lr != self._lr_val:
+            self.lr.fill_(lr)
+            self._lr_val = lr
+        if beta != self._beta_val:
+            self.beta.fill_(beta)
+            self._beta_val = beta
+
+    def _backward_body(self):
+        m = self.model
+        m.flat_grad.zero_()
+        beta_saved, m.beta = m.beta, self.beta
+        try:
+            self.costs = m.losses(self.x, self.r, self.a)
+            self.costs["cost_all"].backward()
+        finally:
+            m.beta = beta_saved
+
+    def _update_body(self):
+        m = self.model
+        m._clip_gradients()
+        m.opt.step_device(self.lr)
+
+    def run(self, x, y_r, a):
+        m = self.model
+        self.x.copy_(x); self.r.copy_(y_r); self.a.copy_(a)
+        self._set_scalars(m.learning_rate, m.beta)
+        self.g_bwd.replay()
+        if self.g_upd is not None:
+            self.allreduce(m.flat_grad)
+            self.g_upd.replay()
+        m.opt.t += 1
+        m.global_step += 1
+        m.last_costs = self.costs
+        return self.costs
 
 
 class NetworkVP_rnn(object):
@@ -205,11 +331,29 @@ class NetworkVP_rnn(object):
         self.beta = cfg.BETA_START
         self.log_epsilon = cfg.LOG_EPSILON
         self.net = PolicyValueNet(cfg, num_actions, seed=seed).to(self.device)
-        self.opt = TFAdam(self.net.parameters())
+        self._flatten()
+        self.opt = TFAdam(self.net.parameters(), self.flat_param, self.flat_grad)
+        self._graphed = {}     # rows -> GraphedTrainStep
+        self.graph_rows = 0    # batches of exactly this many rows are trained from CUDA graphs (enable_graphed_training)
         self.global_step = 0
         self.checkpoints_save_dir = os.environ.get(
             "GA3C_CHECKPOINT_DIR", os.path.join(os.getcwd(), "checkpoints", "RL_tmp"))
         self.last_costs = {}
+
+    def _flatten(self):
+        """All parameters become views into one flat buffer, all gradients views into another: the optimiser and the
+        gradient all-reduce work on single tensors, and gradients accumulate in place (CUDA-graph friendly)."""
+        self.flat_param, self.flat_grad = flatten_parameters(self.net.parameters())
+
+    def enable_graphed_training(self, rows):
+        """Batches of exactly `rows` rows are trained from CUDA graphs from now on (CUDA only; other sizes run eagerly)."""
+        self.graph_rows = int(rows) if self.device.type == "cuda" else 0
+
+    def _clip_gradients(self):
+        if self.cfg.USE_GRAD_CLIP:
+            for p in self.net.parameters():   # tf.clip_by_average_norm
+                avg_norm = p.grad.norm() / p.grad.numel()
+                p.grad.mul_(torch.clamp(self.cfg.GRAD_CLIP_NORM / (avg_norm + 1e-12), max=1.0))
 
     # ---- prediction (GA3C/NetworkVPCore.py:160-176)
     def _as_input(self, x):
@@ -375,37 +519,36 @@ class NetworkVP_rnn(object):
         x = self._as_input(x)
         y_r = self._as_input(y_r)
         a = torch.as_tensor(a, device=self.device)
+        if self.graph_rows and x.shape[0] == self.graph_rows and a.dim() == 1:
+            return self.train_graphed(x, y_r, a)
         costs = self.backward(x, y_r, a)
         self.apply_gradients()
         return costs
 
+    def train_graphed(self, x, y_r, a, allreduce=None):
+        key = (int(x.shape[0]), allreduce is not None)
+        step = self._graphed.get(key)
+        if step is None:
+            step = self._graphed[key] = GraphedTrainStep(self, x.shape[0], allreduce)
+        return step.run(x, y_r, a)
+
     def backward(self, x, y_r, a):
         """Sum-loss gradients of one batch of rows into p.grad for EVERY parameter (an empty batch gives zeros, so that
         ranks with nothing to contribute still take part in the gradient all-reduce)."""
-        params = list(self.net.parameters())
+        self.flat_grad.zero_()    # p.grad are views into it: backward accumulates in place
         if x.shape[0] == 0:
-            for p in params:
-                p.grad = torch.zeros_like(p)
             zero = torch.zeros((), device=self.device)
             self.last_costs = {k: zero for k in ("cost_all", "cost_p", "cost_v", "cost_p_advant_agg", "cost_p_entrop_agg")}
             return self.last_costs
         costs = self.losses(x, y_r, a)
-        for p in params:
-            p.grad = None
         costs["cost_all"].backward()
-        for p in params:
-            if p.grad is None:
-                p.grad = torch.zeros_like(p)
         self.last_costs = costs
         return costs
 
     def apply_gradients(self):
         """tf.clip_by_average_norm (if configured) + the TF-Adam step on whatever is in p.grad (NetworkVPCore.py:100-123);
         the distributed trainer calls it after the gradient all-reduce, so both paths train the same way."""
-        if self.cfg.USE_GRAD_CLIP:
-            for p in self.net.parameters():
-                avg_norm = p.grad.norm() / p.grad.numel()
-                p.grad.mul_(torch.clamp(self.cfg.GRAD_CLIP_NORM / (avg_norm + 1e-12), max=1.0))
+        self._clip_gradients()
         self.opt.step(self.learning_rate)
         self.global_step += 1
 

@@ -14,7 +14,7 @@ import numpy as np
 
 from .Config import get_config
 from .NetworkVP_rnn import NetworkVP_rnn
-from .parallel import allreduce_gradients
+from .parallel import allreduce_flat
 from .rollout import GpuRollout
 from ..scenarios import random_worlds
 
@@ -127,6 +127,8 @@ class Server(object):
         self.rollout.attach_scenario_generator(self._scenario_cfg, self._scenario_seed)   # refill after every step
         self._pending = []
         self._pending_rows = 0
+        if int(getattr(cfg, "GPU_TRAIN_GRAPH", 1)):
+            self.model.enable_graphed_training(self.train_batch_rows())
         self.history = []   # (seconds, episodes, rolling score, optimiser steps, frames) at every stats refresh
 
     def train_batch_rows(self):
@@ -181,9 +183,12 @@ class Server(object):
     def _train_distributed(self, x_, r_, a_):
         """Sum-loss gradients are summed over ranks (== one trainer seeing the concatenation of all ranks' rows)."""
         m = self.model
-        costs = m.backward(m._as_input(x_), m._as_input(r_), self.torch.as_tensor(a_, device=m.device))
-        allreduce_gradients(list(m.net.parameters()))   # fixed parameter list, zeros from ranks without rows
-        m.apply_gradients()                             # clip (if configured) + Adam, as on the single-GPU path
+        x, r, a = m._as_input(x_), m._as_input(r_), self.torch.as_tensor(a_, device=m.device)
+        if m.graph_rows and x.shape[0] == m.graph_rows and a.dim() == 1:
+            return m.train_graphed(x, r, a, allreduce=allreduce_flat)   # graphs around the eager collective
+        costs = m.backward(x, r, a)
+        allreduce_flat(m.flat_grad)     # one flat buffer over EVERY parameter: zeros from ranks without rows
+        m.apply_gradients()             # clip (if configured) + Adam, as on the single-GPU path
         return costs
 
     def save_model(self):

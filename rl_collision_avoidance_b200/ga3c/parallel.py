@@ -5,7 +5,7 @@ The env step itself needs no communication: worlds are independent, each rank ow
   * `gather_rows` + `broadcast_weights`: every rank's emitted rows (x_, r_, a_) are all-gathered (padded to the
     longest, then trimmed) so that the trainer rank sees exactly the concatenation the reference's training_q would
     deliver, and the updated weights are broadcast back;
-  * `allreduce_gradients`: each rank back-propagates its own rows and the sum-loss gradients are summed — the same
+  * `allreduce_flat`: each rank back-propagates its own rows and the sum-loss gradients are summed — the same
     update (the A3C loss is a sum over rows, GA3C/NetworkVPCore.py:71-98) with 0.68 MB instead of the rows on the wire.
 """
 import torch
@@ -51,20 +51,9 @@ def broadcast_weights(parameters, src=0, group=None):
         off += n
 
 
-def allreduce_gradients(parameters, group=None):
-    """Sum gradients over ranks in one flat collective.  The buffer covers EVERY parameter (a missing gradient counts as
-    zeros), so its length is the same on all ranks whatever rows each of them had."""
-    params = list(parameters)
-    for p in params:
-        if p.grad is None:
-            p.grad = torch.zeros_like(p)
-    flat = torch.cat([p.grad.reshape(-1) for p in params])
-    dist.all_reduce(flat, group=group)
-    off = 0
-    for p in params:
-        n = p.numel()
-        p.grad.copy_(flat[off:off + n].view_as(p))
-        off += n
+def allreduce_flat(flat_grad, group=None):
+    """Sum one flat gradient buffer over ranks in place (the parameters' .grad are views into it)."""
+    dist.all_reduce(flat_grad, group=group)
 
 
 def max_over_ranks(value, device, group=None):

@@ -51,16 +51,23 @@ def _worker(rank, world_size, port, tmpdir):
     parallel.broadcast_weights(list(net.net.parameters()), src=0)     # ... until rank 0's weights are broadcast
     if rank == 1:
         pass
-    costs = net.losses(torch.from_numpy(x[lo:hi]), torch.from_numpy(y[lo:hi]), torch.from_numpy(a[lo:hi]))
-    for p in net.net.parameters():
-        p.grad = None
-    costs["cost_all"].backward()
-    parallel.allreduce_gradients(list(net.net.parameters()))
-    net.opt.step(net.learning_rate)
+    net.backward(torch.from_numpy(x[lo:hi]), torch.from_numpy(y[lo:hi]), torch.from_numpy(a[lo:hi]))
+    parallel.allreduce_flat(net.flat_grad)
+    net.apply_gradients()
     ref0 = NetworkVP_rnn("cpu", "network", 11, seed=4)
     ref0.train(x, y, a, 0)
     for k, v in net.net.tf_variables().items():
         np.testing.assert_allclose(v, ref0.net.tf_variables()[k], rtol=0, atol=2e-7, err_msg=k)
+
+    # (2b) a rank with NO rows still takes part: it contributes zeros of the full fixed-length gradient buffer (the
+    # distributed trainer agrees on the number of optimiser steps from the largest row count, so this happens)
+    lo2, hi2 = (0, B) if rank == 0 else (B, B)
+    net.backward(torch.from_numpy(x[lo2:hi2]), torch.from_numpy(y[lo2:hi2]), torch.from_numpy(a[lo2:hi2]))
+    parallel.allreduce_flat(net.flat_grad)
+    net.apply_gradients()
+    ref0.train(x, y, a, 0)
+    for k, v in net.net.tf_variables().items():
+        np.testing.assert_allclose(v, ref0.net.tf_variables()[k], rtol=0, atol=4e-7, err_msg=k)
 
     # (3) sharding and max-over-ranks
     assert parallel.shard_range(524288, rank, world_size) == ((0, 262144) if rank == 0 else (262144, 524288))

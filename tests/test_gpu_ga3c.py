@@ -377,3 +377,43 @@ def test_env_facade_replays_config1_golden():
         env2.step({0: 2})        # missing action for external agent 1 -> KeyError like the reference
     env.close()
     E.set_config(None)
+
+
+def test_graphed_train_step_matches_the_eager_one(phase1_cfg):
+    """NetworkVP_rnn.train on exactly `graph_rows` rows is replayed from CUDA graphs (zero / forward / losses / backward /
+    TF-Adam with learning rate, entropy weight and step count on the device): the weights after several steps with
+    changing data, learning rate and beta are the eager trainer's."""
+    import torch
+    from rl_collision_avoidance_b200.ga3c.NetworkVP_rnn import NetworkVP_rnn
+    cfg = phase1_cfg
+    rng = np.random.default_rng(11)
+    B, L1 = 1024, cfg.NN_INPUT_SIZE
+    avg = np.asarray(cfg.NN_INPUT_AVG_VECTOR, dtype=np.float32)
+    std = np.asarray(cfg.NN_INPUT_STD_VECTOR, dtype=np.float32)
+    eager = NetworkVP_rnn("cuda:0", "network", 11, seed=6)
+    graphed = NetworkVP_rnn("cuda:0", "network", 11, seed=6)
+    graphed.enable_graphed_training(B)
+    start = {k: v.copy() for k, v in eager.net.tf_variables().items()}
+    for step in range(5):
+        x = (avg + std * rng.normal(size=(B, L1))).astype(np.float32)
+        x[:, 0] = rng.integers(0, 4, B)
+        x = torch.from_numpy(x).cuda()
+        y_r = torch.from_numpy(rng.normal(size=B).astype(np.float32)).cuda()
+        a = torch.from_numpy(rng.integers(0, 11, B).astype(np.int32)).cuda()
+        for net in (eager, graphed):
+            net.learning_rate = 1e-3 * (1 + step)          # annealing needs no re-capture
+            net.beta = 1e-4 * (1 + step)
+        c_e = eager.train(x, y_r, a)
+        c_g = graphed.train(x, y_r, a)
+        assert abs(float(c_e["cost_all"]) - float(c_g["cost_all"])) <= 1e-4 * abs(float(c_e["cost_all"])) + 1e-3
+    assert graphed._graphed and graphed.global_step == eager.global_step == 5 and graphed.opt.t == 5
+    ve, vg = eager.net.tf_variables(), graphed.net.tf_variables()
+    for k in ve:
+        moved = np.abs(ve[k] - start[k]).max()
+        assert moved > 1e-4, k
+        np.testing.assert_allclose(vg[k], ve[k], rtol=0, atol=2e-2 * moved + 1e-7, err_msg=k)
+    # a batch of another size falls back to the eager path and keeps the optimiser state consistent
+    x2 = x[:100]
+    graphed.train(x2, y_r[:100], a[:100]); eager.train(x2, y_r[:100], a[:100])
+    assert graphed.opt.t == eager.opt.t == 6
+    np.testing.assert_allclose(graphed.net.tf_variables()["layer2/kernel"], eager.net.tf_variables()["layer2/kernel"], rtol=0, atol=1e-4)

@@ -91,7 +91,7 @@ def test_tf_adam_rule():
     m = v = np.zeros(2); x = np.array([1.0, -2.0])
     for t in range(1, 6):
         g = np.array([0.5 * t, -0.1])
-        w.grad = torch.tensor(g, dtype=torch.float32)
+        w.grad.copy_(torch.tensor(g, dtype=torch.float32))   # .grad is a view into the optimiser's flat buffer
         opt.step(1e-2)
         m = 0.9 * m + 0.1 * g; v = 0.999 * v + 0.001 * g * g
         x = x - 1e-2 * np.sqrt(1 - 0.999 ** t) / (1 - 0.9 ** t) * m / (np.sqrt(v) + 1e-8)
