@@ -317,7 +317,7 @@ typedef struct ca_predictor_params {
 } ca_predictor_params;
 
 /* size of the packed parameter image ca_predictor_pack writes and ca_predict reads (device memory, 128-byte aligned) */
-#define CA_PREDICTOR_BLOB_BYTES 356512
+#define CA_PREDICTOR_BLOB_BYTES 357536
 
 /* Re-pack the parameters into the kernel's shared-memory images (call once per weight update; stream-ordered). */
 int ca_predictor_pack(const ca_predictor_params* params, void* blob, int device, void* stream);

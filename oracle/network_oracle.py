@@ -46,10 +46,12 @@ def _h(a):
 
 
 def forward_fp16_operands(variables, x, avg, std, M, host_len=4, other_len=7, first=1, min_policy=0.0, tanh_rel_err=0.0,
-                          rng=None):
+                          rng=None, value_head_fp32=True):
     """The same network with the ARITHMETIC of the fused predictor kernel (csrc/ca_predict.cu): every operand of a matrix
     product — weights, the normalised inputs, h, the ReLU activations, and the LSTM bias, which rides in the product as a
     weight row — is rounded to fp16; products accumulate in (at least) fp32; dense biases, gates and the softmax are fp32.
+    value_head_fp32 (the kernel since round 2): the value head reads the fullyconnected1 outputs before their fp16
+    rounding and the unrounded logits_v kernel; False reproduces the round-1 kernel (value from the fp16 head product).
     tanh_rel_err > 0 additionally perturbs every tanh by a random relative error of that size (tanh.approx: 2^-11).
     Not bit-exact with the kernel (accumulation order, the hardware's tanh), but it carries the same rounding sources, so
     its distance from `forward` is the error the kernel is expected to have against the fp32 network."""
@@ -84,9 +86,13 @@ def forward_fp16_operands(variables, x, avg, std, M, host_len=4, other_len=7, fi
         h = np.where(live, h_new, h)
     a = np.concatenate([host, _h(h)], axis=1)
     for name in ("layer1", "layer2", "fullyconnected1"):
-        a = _h(np.maximum(a @ _h(variables[name + "/kernel"]) + variables[name + "/bias"], 0.0))
+        a32 = np.maximum(a @ _h(variables[name + "/kernel"]) + variables[name + "/bias"], 0.0)
+        a = _h(a32)
     logits = a @ _h(variables["logits_p/kernel"]) + variables["logits_p/bias"]
-    v = (a @ _h(variables["logits_v/kernel"]) + variables["logits_v/bias"])[:, 0]
+    if value_head_fp32:
+        v = (a32 @ variables["logits_v/kernel"].astype(np.float64) + variables["logits_v/bias"])[:, 0]
+    else:
+        v = (a @ _h(variables["logits_v/kernel"]) + variables["logits_v/bias"])[:, 0]
     e = np.exp(logits - logits.max(axis=1, keepdims=True))
     p = e / e.sum(axis=1, keepdims=True)
     p = (p + min_policy) / (1.0 + min_policy * p.shape[1])

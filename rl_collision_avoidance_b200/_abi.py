@@ -83,7 +83,7 @@ class CaPredictorParams(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in FIELDS]
 
 
-CA_PREDICTOR_BLOB_BYTES = 356512
+CA_PREDICTOR_BLOB_BYTES = 357536
 CA_PREDICT_PLAN_COUNTERS = 64
 CA_PREDICTOR_MAX_OTHERS = 22
 

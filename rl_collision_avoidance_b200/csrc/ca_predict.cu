@@ -50,8 +50,11 @@ constexpr int kOffWOut = kOffWFc1 + 32 * kKgB;        // [32][16][8]: n 0..10 lo
 constexpr int kOffF32 = kOffWOut + 32 * kKgOut;       // float section
 constexpr int kFbLstm = 0, kFbL1 = 256, kFbL2 = 512, kFbFc1 = 768, kFbOut = 1024;  // biases (LSTM: forget bias and the sigmoid 1/2 folded in)
 constexpr int kFAvgO = 1040, kFIstdO = 1048, kFAvgH = 1056, kFIstdH = 1060;        // input normalisation
-constexpr int kF32Count = 1064;
-constexpr int kBlobBytes = kOffF32 + kF32Count * 4;   // 356 512
+constexpr int kFwV = 1064;                            // logits_v kernel in float32 (the value head runs on the CUDA cores)
+constexpr int kF32Count = 1064 + 256;
+constexpr int kBlobBytes = kOffF32 + kF32Count * 4;   // 357 536
+constexpr int kFVpart = kF32Count;                    // shared memory only: the two column halves' partial value sums [2][128]
+constexpr int kF32Smem = kF32Count + 2 * 128;
 static_assert(kBlobBytes == CA_PREDICTOR_BLOB_BYTES, "include/ca_step.h disagrees with the blob layout");
 
 // ---- shared memory carve-up of one CTA ----------------------------------------------------------------------------------
@@ -59,7 +62,7 @@ constexpr int kSmAct = 0;                    // 64 KB: dense activations [32 kg]
                                              //   kg 0..7 = h, kg 8..8+M-1 = x_t, kg 8+M = host, kg 9+M = zeros
 constexpr int kSmW = 32 * kKgA;              // 40 KB weight stage (LSTM / layer1 image, or 2 x 16 KB chunks, or head)
 constexpr int kSmF32 = kSmW + 10 * kKgB;     // float section copy
-constexpr int kSmBar = kSmF32 + ((kF32Count * 4 + 127) / 128) * 128;
+constexpr int kSmBar = kSmF32 + ((kF32Smem * 4 + 127) / 128) * 128;
 constexpr int kSmTotal = kSmBar + 128;       // 12 mbarriers, TMEM base, max sequence length of the tile
 // The 128 KB of a dense layer's weights stream in chunks of kUmmaPerChunk K = 16 products through the 40 KB weight region.
 // The copy path favours large bulk copies: two 16 KB stages (0.208 / 0.184 ms at M = 9 / 3) beat five 8 KB stages
@@ -205,8 +208,16 @@ __device__ __forceinline__ void acc_wait(uint32_t bar, uint32_t& phase, int* err
   tc_fence_after();
 }
 
-// bias + ReLU + fp16 repack of the thread's accumulator row -> activation buffer (the next product's A operand)
-__device__ __forceinline__ void dense_epilogue(uint32_t tmem_row, const float* bias, uint32_t act_row, int half) {
+// bias + ReLU + fp16 repack of the thread's accumulator row -> activation buffer (the next product's A operand).
+// kValue (fullyconnected1 only): the value head is evaluated right here in float32 — the ReLU outputs BEFORE their fp16
+// rounding times the float32 logits_v kernel — and the thread's partial sum over its 128 columns is returned.  The
+// value is what the actors bootstrap their n-step returns from (ProcessAgent.py:71-76) while the trainer evaluates V in
+// float32; the fp16 rounding of the 256 head inputs was the largest single contribution to |dv| (oracle/
+// network_oracle.py, tests/test_network.py): 1.4e-2 -> 1.9e-3 with the trained IROS18 weights.
+template <bool kValue>
+__device__ __forceinline__ float dense_epilogue(uint32_t tmem_row, const float* bias, uint32_t act_row, int half,
+                                                const float* wv = nullptr) {
+  float vacc = 0.f;
   constexpr int kIters = kN / 2 / 32;   // this thread's 128 columns in blocks of 32, loads one block ahead of the math
   float buf[2][32];
   const int cbase = half * (kN / 2);
@@ -228,11 +239,18 @@ __device__ __forceinline__ void dense_epilogue(uint32_t tmem_row, const float* b
       for (int e = 0; e < 4; ++e) {
         const int c = q * 8 + e * 2;
         const float2 b = *reinterpret_cast<const float2*>(bias + c0 + c);
-        w[e] = pack_h2_raw(fminf(fmaxf(a[c] + b.x, 0.f), 60000.f), fminf(fmaxf(a[c + 1] + b.y, 0.f), 60000.f));
+        const float y0 = fminf(fmaxf(a[c] + b.x, 0.f), 60000.f), y1 = fminf(fmaxf(a[c + 1] + b.y, 0.f), 60000.f);
+        if (kValue) {
+          const float2 wvv = *reinterpret_cast<const float2*>(wv + c0 + c);
+          vacc = __fmaf_rn(y0, wvv.x, vacc);
+          vacc = __fmaf_rn(y1, wvv.y, vacc);
+        }
+        w[e] = pack_h2_raw(y0, y1);
       }
       st_shared_v4(act_row + (uint32_t)(c0 / 8 + q) * kKgA, w[0], w[1], w[2], w[3]);
     }
   }
+  return vacc;
 }
 
 __global__ void __launch_bounds__(kThreads, 2) predict_kernel(const Params p) {
@@ -417,7 +435,7 @@ __global__ void __launch_bounds__(kThreads, 2) predict_kernel(const Params p) {
           tma_load(s_w + st * kChunkBytes, wsrc + st * kChunkBytes, kChunkBytes, bar_w0 + 8 * st);
         }
       }
-      dense_epilogue(tmem_row, fsec + (layer == 0 ? kFbL1 : kFbL2), act_row, half);
+      dense_epilogue<false>(tmem_row, fsec + (layer == 0 ? kFbL1 : kFbL2), act_row, half);
       fence_async_smem();
       tc_fence_before();
       __syncthreads();
@@ -455,7 +473,7 @@ __global__ void __launch_bounds__(kThreads, 2) predict_kernel(const Params p) {
       mbar_expect_tx(bar_img, 32 * kKgOut);
       tma_load(s_w, p.blob + kOffWOut, 32 * kKgOut, bar_img);
     }
-    dense_epilogue(tmem_row, fsec + kFbFc1, act_row, half);
+    fsec[kFVpart + half * kRows + r] = dense_epilogue<true>(tmem_row, fsec + kFbFc1, act_row, half, fsec + kFwV);
     fence_async_smem();
     tc_fence_before();
     __syncthreads();
@@ -498,7 +516,7 @@ __global__ void __launch_bounds__(kThreads, 2) predict_kernel(const Params p) {
 #pragma unroll
           for (int a = 0; a < 11; ++a) dst[a] = z[a];
         }
-        if (p.v) p.v[row] = z[11] + bo[11];
+        if (p.v) p.v[row] = (fsec[kFVpart + r] + fsec[kFVpart + kRows + r]) + bo[11];   // float32 value head
         if (p.actions) {
           int act = arg;
           if (!p.greedy) {  // np.random.choice(actions, p=prediction): inverse CDF on one uniform draw
@@ -571,6 +589,7 @@ __global__ void pack_kernel(const PackParams q) {
     f[kFbFc1 + e] = q.b_fc1[e];
   }
   if (e < 16) f[kFbOut + e] = e < 11 ? q.b_p[e] : (e == 11 ? q.b_v[0] : 0.f);
+  if (e < 256) f[kFwV + e] = q.k_v[e];
   if (e < 8) {  // NN input index = observation column - 1: host = 1..4, first other agent = 5..11
     f[kFAvgO + e] = e < 7 ? q.avg[5 + e] : 0.f;
     f[kFIstdO + e] = e < 7 ? 1.f / q.std[5 + e] : 0.f;

@@ -3,10 +3,13 @@ PyTorch fp32 network (`PolicyValueNet`, itself pinned on the NumPy/TF1 oracle in
 test_gpu_ga3c.py::test_fused_lstm_predictor_matches_torch_and_numpy).
 
 The kernel multiplies fp16 operands (11-bit significand, like TF32) with fp32 accumulation and evaluates the LSTM
-gates with `tanh.approx.f32` (2^-11 relative error), so it is compared with a tolerance, stated per test:
-  * observations produced by the env itself (what the rollout feeds it): |dp| <= 5e-3, |dv| <= 5e-3 * (1 + |v|);
+gates with `tanh.approx.f32` (2^-11 relative error); the VALUE head is float32 (fullyconnected1 outputs before their fp16
+rounding times the float32 logits_v kernel, on the CUDA cores).  It is compared with a tolerance, stated per test:
+  * observations produced by the env itself (what the rollout feeds it): |dp| <= 5e-3, |dv| <= 3e-3 * (1 + |v|)
+    (measured with the trained IROS18 weights: dp max 3.8e-3 / p99 1.3e-3, dv max 0.6-2.2e-3 / p99 2.2e-4);
   * synthetic rows drawn from the normalisation statistics, random-init and trained IROS18 weights: |dp| <= 2e-2,
-    |dv| <= 2e-2 * (1 + |v|) (trained weights amplify: |v| reaches ~20 on such out-of-distribution rows).
+    |dv| <= 5e-3 * (1 + |v|) (measured: dp 1.4e-2, dv 2.7e-3 / p99 1e-3 trained; 4e-5 and 3e-4 random-init; with the
+    round-1 fp16 value head dv was 1.4-2e-2; trained weights amplify: |v| reaches ~20 on such out-of-distribution rows).
 Index outputs: the greedy action equals argmax of the kernel's own p bit-exactly, and argmax of the fp32 p wherever the
 fp32 top-2 gap exceeds the p tolerance; sampled actions follow p (chi-square style bound) and are reproducible per
 (seed, offset)."""
@@ -76,7 +79,7 @@ def test_fused_predictor_matches_fp32_network_on_synthetic_rows(phase_cfg, phase
     M = cfg.MAX_NUM_OTHER_AGENTS_OBSERVED
     net = _net(trained)
     obs = _synthetic_obs(cfg, B, M, np.random.default_rng(B))
-    _check(net, torch.from_numpy(obs).cuda(), 2e-2, 2e-2)
+    _check(net, torch.from_numpy(obs).cuda(), 2e-2, 5e-3)
 
 
 @pytest.mark.parametrize("phase", [1, 2])
@@ -98,7 +101,7 @@ def test_fused_predictor_on_env_observations(phase_cfg, phase):
     for t in range(12):
         flat = obs.reshape(W * env.A, env.L)
         if t % 4 == 0:
-            _check(net, flat, 5e-3, 5e-3)
+            _check(net, flat, 5e-3, 3e-3)
         act = torch.randint(0, 11, (W, env.A), generator=gen, device="cuda", dtype=torch.int32)
         obs, _, _, _ = env.step(act)
     env.close()

@@ -116,7 +116,7 @@ def test_checkpoint_round_trip(cfg, tmp_path, monkeypatch):
 
 
 def test_fp16_operand_model_explains_the_fused_predictor_tolerance():
-    """The GPU test of the fused predictor (tests/test_gpu_predictor.py) allows |dp| <= 2e-2 and |dv| <= 2e-2 (1 + |v|) on
+    """The GPU test of the fused predictor (tests/test_gpu_predictor.py) allows |dp| <= 2e-2 and |dv| <= 5e-3 (1 + |v|) on
     synthetic rows with the trained IROS18 weights.  This is the error a network with fp16 PRODUCT OPERANDS and a 2^-11
     tanh has by construction: the NumPy model of the kernel's arithmetic (oracle.network_oracle.forward_fp16_operands)
     shows errors of that size against the float64 network on the same kind of rows — and far smaller ones on random-init
@@ -140,6 +140,11 @@ def test_fp16_operand_model_explains_the_fused_predictor_tolerance():
             dp = np.abs(p16 - p64).max()
             dv = (np.abs(v16 - v64) / (1 + np.abs(v64))).max()
             assert p_lo <= dp <= p_hi, "%s: model policy error %.3e outside [%g, %g]" % (name, dp, p_lo, p_hi)
-            assert dv <= 2e-2, "%s: model value error %.3e" % (name, dv)
+            assert dv <= 5e-3, "%s: model value error %.3e" % (name, dv)      # float32 value head (round 2)
+            if name == "trained":   # the round-1 kernel took the value from the fp16 head product: ~7x the error
+                _, v_old = network_oracle.forward_fp16_operands(variables, x, avg, std, M, tanh_rel_err=2.0 ** -11,
+                                                                rng=np.random.default_rng(1), value_head_fp32=False)
+                dv_old = (np.abs(v_old - v64) / (1 + np.abs(v64))).max()
+                assert 5e-3 < dv_old <= 2e-2 and dv_old > 3 * dv, (dv_old, dv)
     finally:
         cfgmod.set_config(None)
