@@ -221,7 +221,7 @@ const void* pipe_kernel_ptr(int A, int mb, bool dbg = false) {
 // One-shot specialised kernels: (agent slots, min CTAs/SM the register allocation targets).  The second number was
 // picked from -Xptxas -v (largest occupancy without heavy spilling) and, for A = 4, measured on B200:
 // 7 CTAs/SM lets 65 536 x 4 worlds (8192 warp chunks) finish in 2 rounds of 4144 resident warps instead of 3.
-#define CA_ONESHOT_VARIANTS(X) X(2, 8) X(3, 8) X(4, 6) X(4, 7) X(4, 8) X(4, 9) X(5, 6) X(6, 6) X(8, 4) X(8, 5) X(8, 6) X(10, 3) X(10, 4) X(10, 5)
+#define CA_ONESHOT_VARIANTS(X) X(2, 8) X(3, 8) X(4, 6) X(4, 7) X(4, 8) X(4, 9) X(5, 6) X(6, 6) X(8, 4) X(8, 5) X(8, 6) X(10, 3) X(10, 4) X(10, 5) X(10, 6)
 
 int default_oneshot_min_blocks(int A) {
   switch (A) {
@@ -401,6 +401,10 @@ int ca_create(const ca_config* cfg, ca_env** out) {
   DeviceGuard guard(cfg->device);
   if (!guard.ok) return fail(CA_ERR_CUDA, "cudaSetDevice(%d) failed", cfg->device);
 
+  {  // constant tables of the step kernels (per device; idempotent)
+    static const double sincos_table[18] = CA_SINCOS_TABLE;
+    CA_CUDA(cudaMemcpyToSymbol(ca::kSC, sincos_table, sizeof(sincos_table)));
+  }
   ca_env* e = new (std::nothrow) ca_env();
   if (!e) return fail(CA_ERR_ALLOC, "out of host memory");
   e->cfg = *cfg;

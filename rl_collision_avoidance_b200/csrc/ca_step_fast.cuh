@@ -230,7 +230,9 @@ template <int kA, int kMinBlocks, bool kGen>
 __global__ void __launch_bounds__(kBlock, kMinBlocks) ca_step_kernel(const __grid_constant__ Params p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   constexpr int wpw = (32 / kA) < 16 ? (32 / kA) : 16;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  // the warp index through a shuffle: the compiler then treats everything derived from it (chunk, tile and destination
+  // addresses, the operands of the bulk store) as warp-uniform and keeps it on the uniform datapath
+  const int tid = threadIdx.x, lane = tid & 31, warp = __shfl_sync(kFull, tid >> 5, 0);
   const int wl = lane / kA;
   const int i = lane - wl * kA;
   const int base = wl * kA;

@@ -62,7 +62,7 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks) ca_step_stream_kernel(cons
   extern __shared__ __align__(128) unsigned char smem_raw[];
   constexpr int wpw = (32 / kA) < 16 ? (32 / kA) : 16;
   constexpr int kLanesUsed = wpw * kA;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31, warp = __shfl_sync(kFull, threadIdx.x >> 5, 0);   // warp-uniform for the compiler
   const int wl = lane / kA;
   const int i = lane - wl * kA;
   const int base = wl * kA;
