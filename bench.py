@@ -248,16 +248,21 @@ def run_reference_arm(args):
 
 # ---------------------------------------------------------------------------------------------- device-resident steps
 class GraphedSteps(object):
-    """R independent world sets stepped round-robin; G = 2R consecutive steps captured in one CUDA graph, plus one
-    graph per distinct tail length on demand, so that ANY number of steps is replayed without an eager launch."""
+    """R independent world sets (vectorised envs) stepped round-robin over S CUDA streams: step k advances set k mod R on
+    stream (k mod R) mod S, so the steps of one set stay ordered on one stream while steps of different sets — which do
+    not depend on each other — may overlap (the tail of one launch meets the ramp-up of the next: a double-buffered
+    rollout).  S = 1 is the strictly serialised sequence.  All `steps` steps are captured into ONE CUDA graph (fork at
+    the start, S branches, join at the end), so the timed region holds exactly one graph launch for ANY step count:
+    no eager launch, no per-step host work."""
 
-    def __init__(self, sets, device, seed):
+    def __init__(self, sets, device, seed, streams=1):
         import torch
         from rl_collision_avoidance_b200 import _abi
         from rl_collision_avoidance_b200.vec_env import VecCollisionAvoidanceEnv
         self.torch = torch
         W, A = WORLDS_PER_GPU, AGENTS
         self.R = len(sets)
+        self.S = max(1, min(int(streams), self.R))
         self.G = 2 * self.R
         self.envs = []
         for init, nag in sets:
@@ -268,45 +273,51 @@ class GraphedSteps(object):
         gen = torch.Generator(device="cuda")
         gen.manual_seed(seed)
         self.actions = [torch.randint(0, 11, (W, A), dtype=torch.int32, device="cuda", generator=gen) for _ in range(self.G)]
-        self.stream = torch.cuda.Stream()
+        self.streams = [torch.cuda.Stream() for _ in range(self.S)]
+        self.stream = self.streams[0]
         self.graphs = {}
-        with torch.cuda.stream(self.stream):
-            for k in range(self.G):                       # lazy init before capture
+        for k in range(self.G):                           # lazy init before capture, on the stream the set will use
+            with torch.cuda.stream(self.streams[(k % self.R) % self.S]):
                 self._eager(k)
-            self.stream.synchronize()
-        self._graph(self.G)
+        torch.cuda.synchronize()
 
     def _eager(self, k):
         self.envs[k % self.R].step(self.actions[k % self.G])
 
-    def _graph(self, n):
+    def _graph(self, n, S):
         torch = self.torch
-        if n not in self.graphs:
-            with torch.cuda.stream(self.stream):
-                g = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g, stream=self.stream):
+        key = (n, S)
+        if key not in self.graphs:
+            main = self.stream
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.stream(main):
+                with torch.cuda.graph(g, stream=main):
+                    fork = torch.cuda.Event()
+                    fork.record(main)
+                    for st in self.streams[1:S]:
+                        st.wait_event(fork)
                     for k in range(n):
-                        self._eager(k)
+                        with torch.cuda.stream(self.streams[(k % self.R) % S]):
+                            self._eager(k)
+                    for st in self.streams[1:S]:
+                        join = torch.cuda.Event()
+                        join.record(st)
+                        main.wait_event(join)
                 g.replay()                                # upload + first run outside any timed region
-                self.stream.synchronize()
-            self.graphs[n] = g
-        return self.graphs[n]
+                main.synchronize()
+            self.graphs[key] = g
+        return self.graphs[key]
 
-    def run(self, steps, barrier=None):
-        """Replays exactly `steps` steps; returns the device time in ms (CUDA events on the launching stream)."""
+    def run(self, steps, barrier=None, streams=None):
+        """Replays exactly `steps` steps (one graph launch); returns the device time in ms (CUDA events around it)."""
         torch = self.torch
-        n_graph, n_tail = steps // self.G, steps % self.G
-        full = self._graph(self.G)
-        tail = self._graph(n_tail) if n_tail else None
+        g = self._graph(steps, self.S if streams is None else max(1, min(int(streams), self.S)))
         with torch.cuda.stream(self.stream):
             if barrier:
                 barrier()
             ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             ev0.record(self.stream)
-            for _ in range(n_graph):
-                full.replay()
-            if tail is not None:
-                tail.replay()
+            g.replay()
             ev1.record(self.stream)
             self.stream.synchronize()
             if barrier:
@@ -321,26 +332,33 @@ class GraphedSteps(object):
         self.torch.cuda.empty_cache()
 
 
-def env_workload_record(name, rank, local_rank, steps, barrier, max_over_ranks, world_size):
+def env_workload_record(name, rank, local_rank, steps, barrier, max_over_ranks, world_size, streams):
     """One extra env.step workload (device-resident, same method as `value`): a sub-record with its own roofline."""
     saved = WORKLOAD_NAME
     select_workload(name)
     try:
         sets, _ = make_inputs(rank, 6, WORLDS_PER_GPU)
-        gs = GraphedSteps(sets, local_rank, 4321 + rank)
+        gs = GraphedSteps(sets, local_rank, 4321 + rank, streams=streams)
         gs.run(2 * gs.G)
+        gs.run(steps)
         ms = max_over_ranks(gs.run(steps, barrier))
+        gs.run(steps, streams=1)
+        ms1 = max_over_ranks(gs.run(steps, barrier, streams=1))
+        S = gs.S
         gs.close()
         live = live_agents(WORLDS_PER_GPU)
         peak, _ = measured_peak()
         launch_ms = ms / steps
         achieved = ALG_BYTES_PER_AGENT_STEP * live / (launch_ms * 1e-3) / 1e9
+        achieved1 = ALG_BYTES_PER_AGENT_STEP * live / (ms1 / steps * 1e-3) / 1e9
         return {"workload": WORKLOAD, "value": world_size * live * steps / (ms * 1e-3), "unit": "agent-steps/s",
-                "ms_per_step": launch_ms, "steps": steps, "worlds_per_gpu": WORLDS_PER_GPU, "agent_slots": AGENTS,
+                "ms_per_step": launch_ms, "steps": steps, "streams": S, "worlds_per_gpu": WORLDS_PER_GPU, "agent_slots": AGENTS,
                 "live_agents_per_step": live,
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                              "algorithmic_bytes_per_launch": ALG_BYTES_PER_AGENT_STEP * live,
-                             "traffic": ncu_traffic_per_launch(name), "kernel": step_kernel_name()}}
+                             "traffic": ncu_traffic_per_launch(name), "kernel": step_kernel_name()},
+                "single_stream": {"value": world_size * live * steps / (ms1 * 1e-3), "ms_per_step": ms1 / steps,
+                                  "roofline_frac": achieved1 / peak}}
     finally:
         select_workload(saved)
 
@@ -468,14 +486,18 @@ def run_ours(args):
     W, A, K, WU = WORLDS_PER_GPU, AGENTS, args.steps, max(args.warmup, 3)
     R = 6          # ring of world sets: 6 x (19 MB state + 28 MB obs + ...) ~ 300 MB >> 126 MB L2
     sets, rng = make_inputs(rank, R, W)
-    gs = GraphedSteps(sets, local_rank, 1234 + rank)
+    S = max(1, min(args.streams, R))
+    gs = GraphedSteps(sets, local_rank, 1234 + rank, streams=S)
     G = gs.G
     bytes_per_set = 2 * (W // max(1, min(32 // A, 16))) * STATE_BLOCK_BYTES + W * A * 4 + W * A * _abi.obs_len(OTHERS) * 4 + W * A * 9
     sampler = ClockSampler(local_rank)
     launches0 = sum(e.handle.launch_count for e in gs.envs)
     gs.run(max(WU, G))                           # warm-up (>= W steps), same replay path as the timed region
-    gs.run(K)                                    # one untimed pass of exactly the timed pattern (graphs uploaded, clocks up)
-    dev_ms = max_over_ranks(gs.run(K, barrier))  # THE timed region: K steps, graph replays only
+    gs.run(K)                                    # one untimed pass of exactly the timed graph (uploaded, clocks up)
+    dev_ms = max_over_ranks(gs.run(K, barrier))  # THE timed region: K steps = one graph launch
+    # the same K steps strictly serialised on one stream (every launch waits for the previous one): reported beside it
+    gs.run(K, streams=1)
+    dev_ms_1 = max_over_ranks(gs.run(K, barrier, streams=1)) if S > 1 else dev_ms
     eager_launches = sum(e.handle.launch_count for e in gs.envs) - launches0
     gpu_launches = K                             # kernels launched inside the timed region (all from graph replays)
     agent_steps = K * live_agents(W)
@@ -538,8 +560,8 @@ def run_ours(args):
             except Exception as e:   # an extra record must never take the headline down
                 extras[key] = {"error": repr(e)}
             barrier()
-        guarded("phase2_env_step", lambda: env_workload_record("phase2", rank, local_rank, 240, barrier, max_over_ranks, world_size))
-        guarded("ragged_env_step", lambda: env_workload_record("ragged", rank, local_rank, 240, barrier, max_over_ranks, world_size))
+        guarded("phase2_env_step", lambda: env_workload_record("phase2", rank, local_rank, 240, barrier, max_over_ranks, world_size, S))
+        guarded("ragged_env_step", lambda: env_workload_record("ragged", rank, local_rank, 240, barrier, max_over_ranks, world_size, S))
         guarded("rollout_phase2_all_present", lambda: rollout_record("TrainPhase2", 16384, 96, True, local_rank, max_over_ranks, world_size))
         guarded("rollout_phase2_training_mix", lambda: rollout_record("TrainPhase2", 16384, 96, False, local_rank, max_over_ranks, world_size))
         guarded("train_loop", lambda: train_loop_record(args.train_seconds, 65536, local_rank, world_size))
@@ -555,8 +577,12 @@ def run_ours(args):
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": WORKLOAD, "worlds_per_gpu": W, "agents_per_world": A, "others_observed": OTHERS,
                        "obs_len": _abi.obs_len(OTHERS),
-                       "launch": "every timed step replayed from CUDA graphs (%d x %d steps + %d-step tail graph); "
-                                 "%d eager launches before the timed region" % (K // G, G, K % G, eager_launches),
+                       "launch": "all %d timed steps replayed as ONE CUDA graph launch: %d independent world sets (vectorised "
+                                 "envs) stepped round-robin, set r on stream r mod %d (steps of one set stay ordered, "
+                                 "launches of different sets may overlap: the tail of one meets the ramp-up of the next); "
+                                 "single_stream = the same steps strictly serialised on one stream; no eager launch in "
+                                 "the timed region (%d eager + capture launches before it)" % (K, R, S, eager_launches),
+                       "streams": S,
                        "l2": "inputs larger than L2: steps rotate over %d independent world sets (%.0f MB total per GPU)"
                              % (R, R * bytes_per_set / 1e6),
                        "extra_workloads": extras},
@@ -569,7 +595,10 @@ def run_ours(args):
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": ncu_traffic_per_launch(WORKLOAD_NAME), "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": ALG_BYTES_PER_AGENT_STEP * live_agents(W),
-                         "kernel": step_kernel_name(), "launch_ms": launch_ms},
+                         "kernel": step_kernel_name(), "launch_ms": launch_ms,
+                         "frac_single_stream": ALG_BYTES_PER_AGENT_STEP * live_agents(W) / (dev_ms_1 / K * 1e-3) / 1e9 / peak},
+            "single_stream": {"value": world_size * agent_steps / (dev_ms_1 * 1e-3), "unit": "agent-steps/s",
+                              "ms_per_step": dev_ms_1 / K},
         }
         if world_size == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline_run(args.cpu_seconds)
@@ -588,6 +617,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cpu-seconds", type=float, default=10.0, help="wall time of each cpu_baseline sample")
     ap.add_argument("--train-seconds", type=float, default=6.0, help="wall time of the train_loop extra workload")
+    ap.add_argument("--streams", type=int, default=3,
+                    help="CUDA streams the 6 independent world sets are stepped on (1 = strictly serialised launches)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip config.extra_workloads")
     ap.add_argument("--workload", default="phase1", choices=sorted(WORKLOADS),

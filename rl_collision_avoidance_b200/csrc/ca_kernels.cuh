@@ -75,6 +75,7 @@ struct Params {
   int tile_floats;      // floats in the CTA's obs tile = kWarps * wpw * A * L
   int use_bulk_store;   // 1: TMA bulk store of full tiles
   int prefetch_chunks;  // one-shot kernel: L2-prefetch the state block of chunk + prefetch_chunks (0 = off)
+  int prefetch_snapshot;  // specialised kernels: L2-prefetch the snapshot block of a chunk with an ending world (auto-reset)
   int dynamic_sched;    // streaming kernel: 1 = warps pull chunks from *ticket, 0 = strided static schedule
   unsigned* ticket;     // streaming kernel: self-resetting work counter (one per env handle)
   double dt, thr_sq, close_range, r_goal, r_coll, r_step, r_min, r_max, max_heading_change, sensing_horizon;
@@ -91,7 +92,24 @@ struct Params {
   uint8_t* done;           // [W*A]
   uint8_t* over;           // [W]
   int32_t* sidx;           // [W*A*M] or null
+#ifdef CA_TRACE
+  unsigned long long* trace;  // experiment builds only (scripts/step_timeline.py): [n_chunks][8] globaltimer stamps
+#endif
 };
+
+// Timeline stamps of the experiment build (-DCA_TRACE, scripts/step_timeline.py); nothing in the shipped library.
+#ifdef CA_TRACE
+#define CA_STAMP(p, chunk, k, lane, dep)                                                   \
+  do {                                                                                     \
+    if ((lane) == 0) {                                                                     \
+      unsigned long long t_;                                                               \
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_) : "r"((int)(dep)) : "memory");  \
+      (p).trace[(size_t)(chunk) * 8 + (k)] = t_;                                           \
+    }                                                                                      \
+  } while (0)
+#else
+#define CA_STAMP(p, chunk, k, lane, dep) do { } while (0)
+#endif
 
 // Actions table, GCA/envs/policies/GA3C_CADRL/network.py:13-16 (values of the reference's np.mgrid expression)
 __constant__ double kActSpeed[11] = {1.0, 1.0, 1.0, 1.0, 1.0, 0.5, 0.5, 0.5, 0.0, 0.0, 0.0};

@@ -55,6 +55,8 @@ struct DeviceGuard {
 // used by the other translation units of the library (ca_predict.cu) to record a message for ca_last_error()
 int ca_fail_external(int code, const char* msg) { return fail(code, "%s", msg); }
 
+constexpr int kWarpsDefault = 4;
+
 struct ca_env {
   ca_config cfg;
   double step_dt = 0.0;        // dt of the next steps (ca_set_dt); cfg.dt = Config.DT is what reset's time budget uses
@@ -68,6 +70,9 @@ struct ca_env {
   bool dynamic_sched = true;   // streaming kernel: chunks pulled from the ticket counter (CA_STREAM_STATIC=1: strided)
   unsigned* ticket = nullptr;  // streaming kernel: self-resetting work counter
   bool use_pdl = true;         // programmatic dependent launch for step kernels (CA_DISABLE_PDL=1 turns it off)
+  int fast_warps = kWarpsDefault;  // warps per CTA of the one-shot kernel (CA_ONESHOT_WARPS = 1 | 2 | 4)
+  int fast_grid = 0;
+  bool snapshot_prefetch = true;  // early L2 prefetch of the snapshot of ending worlds (CA_DISABLE_SNAPSHOT_PREFETCH=1: off)
   int pipe_min_blocks = 0;     // 0 = default instantiation
   int pipe_grid = 0;
   size_t smem_pipe = 0;
@@ -93,6 +98,9 @@ struct ca_env {
   // staging for the host-side ca_set_world_state / ca_set_reset_state / ca_get_state (lazily allocated, owned by the handle)
   double* d_boundary = nullptr;   // max(W*A*CA_INIT_STRIDE, W*A*CA_STATE_STRIDE) doubles
   int32_t* d_boundary_nag = nullptr;
+#ifdef CA_TRACE
+  unsigned long long* trace = nullptr;  // experiment build: [n_chunks][8] stamps of the last step launch
+#endif
 };
 
 namespace {
@@ -175,6 +183,10 @@ ca::Params make_params(const ca_env* e) {
   p.sensing_horizon = c.sensing_horizon;
   p.s = e->s; p.s0 = e->s0; p.consumed = e->consumed;
   p.ticket = e->ticket; p.dynamic_sched = e->dynamic_sched ? 1 : 0;
+  p.prefetch_snapshot = (c.auto_reset && c.game_over_mode == CA_OVER_ALL_LEARNING_DONE && e->snapshot_prefetch) ? 1 : 0;
+#ifdef CA_TRACE
+  p.trace = e->trace;
+#endif
   return p;
 }
 
@@ -259,11 +271,11 @@ cudaError_t set_fast_smem_attr(int A, int bytes) {
   return cudaSuccess;
 }
 
-int launch_pdl(const void* fn, int grid, size_t smem, cudaStream_t st, ca::Params& p, bool pdl) {
+int launch_pdl(const void* fn, int grid, size_t smem, cudaStream_t st, ca::Params& p, bool pdl, int threads = kBlock) {
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3(grid);
-  cfg.blockDim = dim3(kBlock);
+  cfg.blockDim = dim3(threads);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
@@ -289,7 +301,7 @@ int launch_world_kernel(ca_env* e, bool step, ca::Params& p, cudaStream_t st) {
   } else if (step && has_fast_kernel(e)) {
     p.use_bulk_store = e->bulk_ok ? 1 : 0;  // the kernel aligns the tile to the destination's 16-byte phase itself
     p.prefetch_chunks = e->prefetch_chunks;
-    rc = launch_pdl(fast_kernel_ptr(e->A, dbg), e->grid, e->smem_fast, st, p, e->use_pdl);
+    rc = launch_pdl(fast_kernel_ptr(e->A, dbg), e->fast_grid, e->smem_fast, st, p, e->use_pdl, e->fast_warps * 32);
   } else if (step) {
     rc = launch_pdl((const void*)ca::ca_world_kernel<true>, e->grid, e->smem_bytes, st, p, e->use_pdl);
   } else {
@@ -419,7 +431,13 @@ int ca_create(const ca_config* cfg, ca_env** out) {
   const size_t tile_bytes = (((size_t)e->tile_floats * 4 + 127) / 128) * 128;
   const int nkeys = cfg->sort_method == CA_SORT_TIME_TO_IMPACT ? 4 : 3;
   e->smem_bytes = tile_bytes + (size_t)nkeys * e->A * kBlock * sizeof(double);
-  e->smem_fast = (size_t)kWarps * ca::warp_tile_region(e->tile_floats / kWarps);
+  {  // the warps of the one-shot kernel are independent workers: fewer warps per CTA = finer-grained slot reuse
+    const char* fw = getenv("CA_ONESHOT_WARPS");
+    const int v = fw ? atoi(fw) : 0;
+    if (v == 1 || v == 2 || v == 4) e->fast_warps = v;
+  }
+  e->fast_grid = (int)((e->n_chunks + e->fast_warps - 1) / e->fast_warps);
+  e->smem_fast = (size_t)e->fast_warps * ca::warp_tile_region(e->tile_floats / kWarps);
   const char* nb = getenv("CA_DISABLE_BULK_STORE");
   e->bulk_ok = !(nb && nb[0] == '1');
   const char* fg = getenv("CA_FORCE_GENERIC");
@@ -437,11 +455,12 @@ int ca_create(const ca_config* cfg, ca_env** out) {
   if (ce == cudaSuccess) ce = set_fast_smem_attr(e->A, (int)e->smem_fast);
   if (ce == cudaSuccess && has_fast_kernel(e)) {  // how many CTAs of the one-shot kernel are resident at once
     int per_sm = 0, sms = 0;
-    ce = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fast_kernel_ptr(e->A, false), kBlock, e->smem_fast);
+    ce = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fast_kernel_ptr(e->A, false), e->fast_warps * 32, e->smem_fast);
     if (ce == cudaSuccess) ce = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, cfg->device);
     const char* pf = getenv("CA_DISABLE_L2_PREFETCH");
-    if (ce == cudaSuccess && !(pf && pf[0] == '1') && (long)per_sm * sms < (long)e->grid)
-      e->prefetch_chunks = per_sm * sms * kWarps;
+    if (ce == cudaSuccess && !(pf && pf[0] == '1') && (long)per_sm * sms < (long)e->fast_grid)
+      e->prefetch_chunks = per_sm * sms * e->fast_warps;
+    if (getenv("CA_VERBOSE")) fprintf(stderr, "[ca] one-shot kernel: %d warps/CTA, %d CTAs/SM resident, grid %d\n", e->fast_warps, per_sm, e->fast_grid);
   }
   const char* kc = getenv("CA_STEP_KERNEL");  // "oneshot" (default) | "pipe" | "generic"
   if (kc && strcmp(kc, "oneshot") == 0) e->kernel_choice = 1;
@@ -450,6 +469,8 @@ int ca_create(const ca_config* cfg, ca_env** out) {
   e->dynamic_sched = !(ss && ss[0] == '1');
   const char* np = getenv("CA_DISABLE_PDL");
   e->use_pdl = !(np && np[0] == '1');
+  const char* sp = getenv("CA_DISABLE_SNAPSHOT_PREFETCH");
+  e->snapshot_prefetch = !(sp && sp[0] == '1');
   if (kc && strcmp(kc, "generic") == 0) e->force_generic = true;
   if (ce == cudaSuccess && has_fast_kernel(e)) {
     e->pipe_min_blocks = default_pipe_min_blocks(e->A);
@@ -489,9 +510,23 @@ int ca_create(const ca_config* cfg, ca_env** out) {
   carve(e);
   cudaMemset(e->consumed, 0, (size_t)e->W);
   cudaMemset(e->ticket, 0, 128);
+#ifdef CA_TRACE
+  cudaMalloc(&e->trace, (size_t)e->n_chunks * 64);
+  cudaMemset(e->trace, 0, (size_t)e->n_chunks * 64);
+#endif
   *out = e;
   return CA_OK;
 }
+
+#ifdef CA_TRACE
+// experiment build only (scripts/step_timeline.py): the stamps of the handle's last step launch -> host
+int ca_trace_read(ca_env* e, unsigned long long* out) {
+  DeviceGuard guard(e->cfg.device);
+  CA_CUDA(cudaDeviceSynchronize());
+  CA_CUDA(cudaMemcpy(out, e->trace, (size_t)e->n_chunks * 64, cudaMemcpyDeviceToHost));
+  return CA_OK;
+}
+#endif
 
 int ca_destroy(ca_env* e) {
   if (!e) return CA_OK;

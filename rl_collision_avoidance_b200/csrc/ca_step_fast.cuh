@@ -223,6 +223,31 @@ __device__ __forceinline__ bool warp_tile_store(const Params& p, float* dst, con
   return false;
 }
 
+// Worlds in which no learning agent is still running after the move (goal reached, time budget spent, or done before
+// this step) end in this step whatever the collision test says, and with auto-reset reload their snapshot block — a
+// cold DRAM read in the middle of the chunk, ~8 % of the chunks of a training batch, and the warps that pay it are the
+// tail of the launch.  Pull that block towards L2 now (one TMA bulk prefetch per warp, SASS UBLKPF): the all-pairs pass
+// and the reward run while it is in flight.  Episodes ended by a collision in this very step are not caught here.
+__device__ __forceinline__ void prefetch_snapshot_if_ending(const Params& p, const Agent& a, bool world_ok, bool valid,
+                                                            unsigned gmask, const double* blk0, int lane) {
+  if (!p.prefetch_snapshot) return;
+  const bool learning = valid && (a.policy == CA_POLICY_LEARNING_GA3C || a.policy == CA_POLICY_LEARNING);
+  const unsigned running = __ballot_sync(kFull, learning && !(a.flags & CA_F_DONE_MASK));
+  if (__any_sync(kFull, world_ok && (running & gmask) == 0u) && lane == 0)
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(blk0), "r"(kBlkReadBytes) : "memory");
+}
+
+// The grid runs in about two rounds of resident CTAs: pull the state block and the actions of the chunk that will run in
+// this warp's slot one round later into L2 (TMA bulk prefetch), so the second round does not start with another DRAM
+// round trip.
+__device__ __forceinline__ void prefetch_next_round(const Params& p, int chunk, int wpw, int kA, int lane) {
+  const int pc = chunk + p.prefetch_chunks;
+  if (lane == 0 && pc * wpw < p.W) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(blk_ptr(p.s, pc)), "r"(kBlkReadBytes) : "memory");
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(p.actions + (size_t)pc * wpw * kA) : "memory");
+  }
+}
+
 // bytes of shared memory per warp for the observation tile: rows + 16 bytes of phase room, 16-byte granular
 __host__ __device__ __forceinline__ int warp_tile_region(int tile_floats) { return ((tile_floats * 4 + 15) / 16) * 16 + 16; }
 
@@ -237,16 +262,12 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks) ca_step_kernel(const __gri
   const int i = lane - wl * kA;
   const int base = wl * kA;
   // 32-bit indexing: ca_create refuses W * A >= 2^31
-  const int chunk = blockIdx.x * kWarps + warp;
+  const int chunk = blockIdx.x * (int)(blockDim.x >> 5) + warp;   // 1, 2 or 4 warps per CTA (ca_step.cu: fast_warps)
   const int first_world_warp = chunk * wpw;
   const int w = first_world_warp + wl;
   const bool world_ok = wl < wpw && w < p.W;
   const unsigned g = world_ok ? (unsigned)w * kA + i : 0u;
   double* const blk = blk_ptr(p.s, chunk);
-  pdl_wait();                // nothing produced by the previous kernel is read above this line
-  pdl_launch_dependents();
-  int n = world_ok ? blk_nag(blk)[wl] : 0;
-  bool valid = world_ok && i < n;
   const unsigned gmask = (kA >= 32 ? kFull : ((1u << kA) - 1u)) << (base & 31);
 
   // per-warp tile: rows of the warp's wpw worlds, assembled at the 16-byte phase of their destination
@@ -257,17 +278,25 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks) ca_step_kernel(const __gri
   float* row = wtile + shift + (wl * kA + i) * p.L;
   int32_t* sidx_row = (kGen && p.sidx && world_ok) ? p.sidx + (size_t)g * p.M : nullptr;
 
+  CA_STAMP(p, chunk, 0, lane, 0);
+  pdl_wait();                // nothing produced by the previous kernel is read above this line
+  pdl_launch_dependents();
+  CA_STAMP(p, chunk, 1, lane, 0);
   // The state loads do not wait for the agent count: every slot of an existing world is loaded (absent slots hold
   // zeros / stale values and are discarded below), so only ONE DRAM round trip is exposed instead of two.
   Agent a;
-  int act = 0;
+  int n = 0, act = 0;
   if (world_ok) {
+    n = blk_nag(blk)[wl];
     load_agent<false>(blk, lane, a);
     act = p.actions[g];
   }
+  bool valid = world_ok && i < n;
   if (!valid) { zero_agent(a); act = 0; }
 
   step_take_action<kGen>(p, a, act, g, valid);
+  CA_STAMP(p, chunk, 2, lane, a.flags);
+  if (!kGen) prefetch_snapshot_if_ending(p, a, world_ok, valid, gmask, blk_ptr(p.s0, chunk), lane);
 
   Ego e = ego_frame(a.px, a.py, a.gx, a.gy, a.hd);
   OthersLite<kA> o;
@@ -276,19 +305,12 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks) ca_step_kernel(const __gri
   const int nm1 = others_bound<kA>(n);
   fast_pair_pass<kA, true, kGen>(p, a, e, valid, n, nm1, i, base, o, coll, nearest);
 
-  if (p.prefetch_chunks > 0 && lane == 0) {
-    // The grid runs in about two rounds of resident CTAs.  By now this round's own load burst has drained and DRAM is
-    // idle while the warps compute: pull the state block and the actions of the chunk that will run in this slot one
-    // round later into L2 (TMA bulk prefetch), so the second round does not start with another DRAM burst.
-    const int pc = chunk + p.prefetch_chunks;
-    if (pc * wpw < p.W) {
-      asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(blk_ptr(p.s, pc)), "r"(kBlkReadBytes) : "memory");
-      asm volatile("prefetch.global.L2 [%0];" ::"l"(p.actions + (size_t)pc * wpw * kA) : "memory");
-    }
-  }
+  // by now this round's own load burst has drained and DRAM is idle while the warps compute
+  if (p.prefetch_chunks > 0) prefetch_next_round(p, chunk, wpw, kA, lane);
 
   bool dn, over;
   const float r = step_reward_done<kGen>(p, a, valid, i, coll, nearest, gmask, dn, over);
+  CA_STAMP(p, chunk, 3, lane, __float_as_int(r));
   if (world_ok) {
     p.reward[g] = r;
     p.done[g] = dn ? 1 : 0;
@@ -321,12 +343,17 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks) ca_step_kernel(const __gri
     fast_write_obs_row<kA, kGen>(p, a, e, world_ok, valid, nm1r, i, base, o, row, sidx_row, wtile, (tile_floats + 7) & ~3);
   }
 
+  CA_STAMP(p, chunk, 4, lane, 0);
   const int worlds_left = p.W - first_world_warp;
   if (worlds_left > 0) {
     const int nf = (worlds_left < wpw ? worlds_left : wpw) * kA * p.L;
     if (warp_tile_store(p, dst, wtile + shift, shift, nf, lane) && lane == 0)
       asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // the tile must outlive the store's reads
   }
+  CA_STAMP(p, chunk, 5, lane, 0);
+#ifdef CA_TRACE
+  if (lane == 0) { unsigned sm_; asm volatile("mov.u32 %0, %%smid;" : "=r"(sm_)); p.trace[(size_t)chunk * 8 + 6] = sm_; p.trace[(size_t)chunk * 8 + 7] = 0; }
+#endif
 }
 
 }  // namespace ca

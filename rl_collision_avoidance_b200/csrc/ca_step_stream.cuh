@@ -89,15 +89,22 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks) ca_step_stream_kernel(cons
   pdl_launch_dependents();
   if (gw >= n_chunks) return;
 
-  // loads of chunk c: the whole state block by ONE bulk copy into the stage, the caller's action into a register
-  int pf_act = 0;
+  // loads of chunk c: the whole state block by ONE bulk copy into the stage; the caller's actions are only pulled into
+  // L2 here (a register holding them across the whole iteration was spilled at 72 registers, which made the warp wait
+  // for the load at once) and are loaded at the end of the iteration, just before the tile store
   auto prefetch = [&](int c) {
-    const int w = c * wpw + wl;
-    pf_act = (lane_used && w < p.W) ? p.actions[(unsigned)w * kA + i] : 0;
     if (lane == 0) {
       mbar_arrive_expect_tx(bar, kBlkReadBytes);
       tma_load_1d(stage, blk_ptr(p.s, c), kBlkReadBytes, bar);
     }
+    if (lane < 2) {  // the chunk's wpw * kA actions: at most two 128-byte lines
+      const int32_t* a0 = p.actions + (size_t)c * kLanesUsed;
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(lane == 0 ? a0 : a0 + kLanesUsed - 1) : "memory");
+    }
+  };
+  auto load_action = [&](int c) {
+    const int w = c * wpw + wl;
+    return (lane_used && w < p.W) ? p.actions[(unsigned)w * kA + i] : 0;
   };
   // draw the next ticket (lane 0; the result is consumed one chunk later, so its latency is hidden)
   int ticket = 0;
@@ -112,6 +119,7 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks) ca_step_stream_kernel(cons
   int c = gw;
   int static_next = gw + GW;  // schedule without the counter (p.dynamic_sched = 0): strided
   prefetch(c);
+  int act_next = load_action(c);
   draw();
 
   while (true) {
@@ -123,13 +131,15 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks) ca_step_stream_kernel(cons
     int32_t* sidx_row = (kGen && p.sidx && world_ok) ? p.sidx + (size_t)g * p.M : nullptr;
 
     // the chunk's block has landed in the stage (padded blocks make partial last chunks loadable too)
+    CA_STAMP(p, c, 0, lane, 0);
     mbar_wait(bar, parity);
     parity ^= 1u;
+    CA_STAMP(p, c, 1, lane, 0);
     int n = world_ok ? blk_nag(stage)[wl] : 0;
     bool valid = world_ok && i < n;
     Agent a;
     if (valid) load_agent<false>(stage, lane, a); else zero_agent(a);
-    const int act = valid ? pf_act : 0;
+    const int act = valid ? act_next : 0;
     __syncwarp();  // every lane has copied its state out of the stage: it may be refilled
 
     // next chunk of this warp: the ticket drawn one iteration ago
@@ -149,6 +159,8 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks) ca_step_stream_kernel(cons
     }
 
     step_take_action<kGen>(p, a, act, g, valid);
+    CA_STAMP(p, c, 2, lane, a.flags);
+    if (!kGen) prefetch_snapshot_if_ending(p, a, world_ok, valid, gmask, blk_ptr(p.s0, c), lane);
 
     Ego e = ego_frame(a.px, a.py, a.gx, a.gy, a.hd);
     OthersLite<kA> o;
@@ -159,6 +171,7 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks) ca_step_stream_kernel(cons
 
     bool dn, over;
     const float r = step_reward_done<kGen>(p, a, valid, i, coll, nearest, gmask, dn, over);
+    CA_STAMP(p, c, 3, lane, __float_as_int(r));
     if (world_ok) {
       p.reward[g] = r;
       p.done[g] = dn ? 1 : 0;
@@ -200,10 +213,16 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks) ca_step_stream_kernel(cons
       fast_write_obs_row<kA, kGen>(p, a, e, world_ok, valid, nm1r, i, base, o, row, sidx_row, wtile, (tile_floats + 7) & ~3);
     }
 
+    if (more) act_next = load_action(nxt);   // an L2 hit by now; consumed after the next chunk's barrier wait
     // ---- observation tile -> global (the wait for the store is deferred to the next chunk)
+    CA_STAMP(p, c, 4, lane, 0);
     const int worlds_left = p.W - first_world;
     const int nf = (worlds_left < wpw ? worlds_left : wpw) * kA * p.L;
     store_pending = warp_tile_store(p, dst, wtile + shift, shift, nf, lane);
+    CA_STAMP(p, c, 5, lane, 0);
+#ifdef CA_TRACE
+    if (lane == 0) { unsigned sm_; asm volatile("mov.u32 %0, %%smid;" : "=r"(sm_)); p.trace[(size_t)c * 8 + 6] = sm_; p.trace[(size_t)c * 8 + 7] = (unsigned)gw; }
+#endif
     if (!more) break;
     c = nxt;
   }
