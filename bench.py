@@ -316,6 +316,9 @@ class GraphedSteps(object):
             if barrier:
                 barrier()
             ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            # ~0.2 ms of device-side spinning first, so that the events and the graph launch are all enqueued before the
+            # device reaches them: no host latency lands inside the timed region, however short it is (--steps 20)
+            torch.cuda._sleep(400000)
             ev0.record(self.stream)
             g.replay()
             ev1.record(self.stream)

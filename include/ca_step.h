@@ -146,7 +146,9 @@ int ca_destroy(ca_env* env);
 
 /* Inject the initial configuration of every world (≙ env.set_agents + Agent.__init__) and reset.
  * init: double[W][A][CA_INIT_STRIDE]; num_agents: int32[W] with 1 <= n_w <= A (rows >= n_w ignored).
- * on_device != 0: both pointers are device pointers (copied stream-ordered on `stream`). */
+ * on_device != 0: both pointers are device pointers (copied stream-ordered on `stream`).
+ * Either way the call returns after `stream` has drained (it reads back whether every world has all A agents, which
+ * selects the step kernel's loop rendering); not capturable into a CUDA graph. */
 int ca_set_world_state(ca_env* env, const double* init, const int32_t* num_agents, int on_device, void* stream);
 
 /* Replace only the reset snapshot (same tensors as ca_set_world_state): live worlds keep running and pick the new

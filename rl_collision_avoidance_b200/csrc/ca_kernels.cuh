@@ -75,6 +75,7 @@ struct Params {
   int tile_floats;      // floats in the CTA's obs tile = kWarps * wpw * A * L
   int use_bulk_store;   // 1: TMA bulk store of full tiles
   int prefetch_chunks;  // one-shot kernel: L2-prefetch the state block of chunk + prefetch_chunks (0 = off)
+  int all_present;      // host-side hint: every world has all A agents (ca_step.cu); the kernels still check per warp
   int prefetch_snapshot;  // specialised kernels: L2-prefetch the snapshot block of a chunk with an ending world (auto-reset)
   int dynamic_sched;    // streaming kernel: 1 = warps pull chunks from *ticket, 0 = strided static schedule
   unsigned* ticket;     // streaming kernel: self-resetting work counter (one per env handle)

@@ -72,6 +72,11 @@ struct ca_env {
   bool use_pdl = true;         // programmatic dependent launch for step kernels (CA_DISABLE_PDL=1 turns it off)
   int fast_warps = kWarpsDefault;  // warps per CTA of the one-shot kernel (CA_ONESHOT_WARPS = 1 | 2 | 4)
   int fast_grid = 0;
+  // host-side knowledge "every world has all A agents, live state and snapshot alike" (host-provided agent counts, or a
+  // generator configured with min_agents == max_agents == A): the step launch then takes the instantiation of the
+  // per-other loops without bound checks; anything unknown (device-resident counts) or ragged takes the bounded one.
+  // Launch-uniform on purpose: the two renderings of a 10-agent step do not fit the instruction cache together.
+  bool all_present_live = false, all_present_snapshot = false;
   bool snapshot_prefetch = true;  // early L2 prefetch of the snapshot of ending worlds (CA_DISABLE_SNAPSHOT_PREFETCH=1: off)
   int pipe_min_blocks = 0;     // 0 = default instantiation
   int pipe_grid = 0;
@@ -112,7 +117,7 @@ using ca::kWarps;
 // agent.py:29-136.
 __global__ void unpack_init_kernel(const double* __restrict__ init, const int32_t* __restrict__ nag_in, ca::StateBlocks s,
                                    ca::StateBlocks s0, int W, int A, double max_time_ratio, double thr, double dt,
-                                   bool snapshot_only) {
+                                   bool snapshot_only, unsigned* ragged_flag) {
   const long g = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (g >= (long)W * A) return;
   const int w = (int)(g / A), i = (int)(g - (long)w * A);
@@ -126,6 +131,7 @@ __global__ void unpack_init_kernel(const double* __restrict__ init, const int32_
   if (i == 0) {
     ca::blk_nag(b0)[wl] = n;
     if (!snapshot_only) ca::blk_nag(b)[wl] = n;
+    if (n != A) *ragged_flag = 1u;   // some world has fewer than A agents (read back by set_state_impl)
   }
   double v[CA_INIT_STRIDE];
 #pragma unroll
@@ -183,6 +189,7 @@ ca::Params make_params(const ca_env* e) {
   p.sensing_horizon = c.sensing_horizon;
   p.s = e->s; p.s0 = e->s0; p.consumed = e->consumed;
   p.ticket = e->ticket; p.dynamic_sched = e->dynamic_sched ? 1 : 0;
+  p.all_present = (e->all_present_live && e->all_present_snapshot) ? 1 : 0;
   p.prefetch_snapshot = (c.auto_reset && c.game_over_mode == CA_OVER_ALL_LEARNING_DONE && e->snapshot_prefetch) ? 1 : 0;
 #ifdef CA_TRACE
   p.trace = e->trace;
@@ -295,6 +302,8 @@ int launch_world_kernel(ca_env* e, bool step, ca::Params& p, cudaStream_t st) {
   // production instantiation: everything the GA3C training configs use; anything else takes the general one
   const bool dbg = p.sidx != nullptr || std::isfinite(e->cfg.sensing_horizon) || e->M != e->A - 1 || p.cont != nullptr ||
                    e->cfg.game_over_mode != CA_OVER_ALL_LEARNING_DONE || e->cfg.sort_method != CA_SORT_CLOSEST_FIRST;
+  if (step && e->cfg.auto_reset && !e->all_present_snapshot) e->all_present_live = false;   // worlds may adopt ragged snapshots
+  if (!step) e->all_present_live = p.mask ? (e->all_present_live && e->all_present_snapshot) : e->all_present_snapshot;
   if (step && has_fast_kernel(e) && e->kernel_choice == 0) {
     p.use_bulk_store = e->bulk_ok ? 1 : 0;  // the kernel aligns the tile to the destination's 16-byte phase itself
     rc = launch_pdl(pipe_kernel_ptr(e->A, e->pipe_min_blocks, dbg), e->pipe_grid, e->smem_pipe, st, p, e->use_pdl);
@@ -549,10 +558,13 @@ static int set_state_impl(ca_env* e, const double* init, const int32_t* num_agen
   const size_t n = (size_t)e->W * e->A;
   const double* d_init = init;
   const int32_t* d_nag = num_agents;
+  bool all_present = !on_device;   // device-resident counts: answered by the unpack kernel below
   if (!on_device) {
-    for (int w = 0; w < e->W; ++w)
+    for (int w = 0; w < e->W; ++w) {
       if (num_agents[w] < 1 || num_agents[w] > e->A)
         return fail(CA_ERR_INVALID_ARG, "num_agents[%d] = %d outside 1..%d", w, num_agents[w], e->A);
+      all_present = all_present && num_agents[w] == e->A;
+    }
     const int rc = ensure_boundary(e);   // handle-owned staging: nothing to free on the error paths below
     if (rc != CA_OK) return rc;
     CA_CUDA(cudaMemcpyAsync(e->d_boundary, init, n * CA_INIT_STRIDE * sizeof(double), cudaMemcpyHostToDevice, st));
@@ -562,12 +574,22 @@ static int set_state_impl(ca_env* e, const double* init, const int32_t* num_agen
   }
   const int threads = 256;
   const int blocks = (int)((n + threads - 1) / threads);
+  unsigned* const ragged_flag = e->ticket + 16;   // a spare word of the handle's 128-byte counter block
+  if (on_device) CA_CUDA(cudaMemsetAsync(ragged_flag, 0, sizeof(unsigned), st));
   unpack_init_kernel<<<blocks, threads, 0, st>>>(d_init, d_nag, e->s, e->s0, e->W, e->A, e->cfg.max_time_ratio,
-                                                 e->cfg.near_goal_threshold, e->cfg.dt, snapshot_only);
+                                                 e->cfg.near_goal_threshold, e->cfg.dt, snapshot_only, ragged_flag);
   CA_CUDA(cudaPeekAtLastError());
   e->launches += 1;
-  if (!on_device) CA_CUDA(cudaStreamSynchronize(st));   // the staging may be reused by the next call
-  if (!snapshot_only) e->initialised = true;
+  if (on_device) {   // device-resident counts: the kernel reports whether every world has all A agents
+    unsigned ragged = 1u;
+    CA_CUDA(cudaMemcpyAsync(&ragged, ragged_flag, sizeof(unsigned), cudaMemcpyDeviceToHost, st));
+    CA_CUDA(cudaStreamSynchronize(st));
+    all_present = ragged == 0u;
+  } else {
+    CA_CUDA(cudaStreamSynchronize(st));   // the staging may be reused by the next call
+  }
+  e->all_present_snapshot = all_present;
+  if (!snapshot_only) { e->initialised = true; e->all_present_live = all_present; }
   return CA_OK;
 }
 
@@ -754,6 +776,10 @@ int ca_generate_scenarios(ca_env* e, const ca_scenario_config* c, uint64_t seed,
   ca::generate_scenarios_kernel<<<(e->W + ca::kGenWarps - 1) / ca::kGenWarps, ca::kGenWarps * 32, 0, (cudaStream_t)stream>>>(p);
   CA_CUDA(cudaPeekAtLastError());
   e->launches += 1;
+  {
+    const bool fixed = c->min_agents == e->A && c->max_agents == e->A;
+    e->all_present_snapshot = only_consumed ? (e->all_present_snapshot && fixed) : fixed;
+  }
   if (!e->initialised && !only_consumed) {
     // first use without ca_set_world_state: the generated snapshot defines the worlds; the caller must ca_reset (all
     // worlds) before stepping.  Live worlds of an initialised handle are never touched by the generator.

@@ -39,7 +39,9 @@ __device__ __forceinline__ int others_bound(int n) {
 // kGen selects the general variant (finite SENSING_HORIZON, neighbour-index output for parity tests, M < kA - 1
 // clipping); the production instantiation (kGen = false) carries neither their instructions nor their registers.
 // First loop of the sensor (OtherAgentsStatesSensor.sense :72-103) fused with _check_for_collisions (:370-409).
-template <int kA, bool kCollide, bool kGen>
+// kAll: every world of the warp has all kA agents (nm1 == kA - 1): the instantiation without the per-iteration bound
+// checks (and without the register copies their control-flow joins cost) — TrainPhase1 / all-present batches.
+template <int kA, bool kCollide, bool kGen, bool kAll>
 __device__ __forceinline__ void fast_pair_pass(const Params& p, const Agent& a, const Ego& e, bool valid, int n, int nm1,
                                                int i, int base, OthersLite<kA>& o, bool& coll, double& nearest) {
   coll = false;
@@ -50,7 +52,7 @@ __device__ __forceinline__ void fast_pair_pass(const Params& p, const Agent& a, 
     o.key[k] = INT_MAX;
     o.po[k] = 0.0;
     o.pprl[k] = 0.f; o.d2o[k] = 0.f;
-    if (kA >= 6 && k >= nm1) continue;   // warp-uniform
+    if (!kAll && k >= nm1) continue;   // warp-uniform
     const int j = k + (k >= i ? 1 : 0);
     const int src = (base + j) & 31;
     const double xj = shfl_d(a.px, src), yj = shfl_d(a.py, src), rj = shfl_d(a.rad, src);
@@ -76,18 +78,33 @@ __device__ __forceinline__ bool key_first(int q1, double p1, int q2, double p2) 
   return (q1 < q2) || (q1 == q2 && p1 <= p2);
 }
 
-// slot[k] = number of keys among the first kUse that sort before key k (stable: equal keys keep index order); each
-// unordered pair is compared once
+// slot[k] += number of keys among the first kUse that sort before key k (stable: equal keys keep index order); each
+// unordered pair is compared once.  b(k1, k2) = key_first(k1, k2) for k1 < k2; with L[k] = sum_{k1<k} b(k1, k) and
+// W[k] = sum_{k2>k} b(k, k2) the rank is L[k] + (kUse - 1 - k) - W[k].  The comparison is written as three chained
+// predicate instructions (setp.eq -> setp.le.and.f64 -> setp.lt.or) and two predicated adds per pair; the compiler's own
+// rendering of the boolean expression plus two selects cost ~11 instructions per pair (20 % of the 10-agent kernel).
 template <int kN, int kUse>
 __device__ __forceinline__ void rank_pairs(const int* key, const double* po, int* slot) {
+  int L[kN], Wn[kN];
+#pragma unroll
+  for (int k = 0; k < kN; ++k) { L[k] = 0; Wn[k] = 0; }
 #pragma unroll
   for (int k1 = 0; k1 < kUse; ++k1)
 #pragma unroll
     for (int k2 = k1 + 1; k2 < kUse; ++k2) {
-      const bool b = key_first(key[k1], po[k1], key[k2], po[k2]);
-      slot[k1] += b ? 0 : 1;
-      slot[k2] += b ? 1 : 0;
+      asm("{\n\t"
+          ".reg .pred peq, ple, pb;\n\t"
+          "setp.eq.s32 peq, %2, %3;\n\t"
+          "setp.le.and.f64 ple, %4, %5, peq;\n\t"
+          "setp.lt.or.s32 pb, %2, %3, ple;\n\t"
+          "@pb add.s32 %0, %0, 1;\n\t"
+          "@pb add.s32 %1, %1, 1;\n\t"
+          "}"
+          : "+r"(L[k2]), "+r"(Wn[k1])
+          : "r"(key[k1]), "r"(key[k2]), "d"(po[k1]), "d"(po[k2]));
     }
+#pragma unroll
+  for (int k = 0; k < kUse; ++k) slot[k] += L[k] - Wn[k] + (kUse - 1 - k);
 }
 // the same with the (warp-uniform) number of keys in use known only at run time: one fully unrolled body per count
 template <int kN, int kUse>
@@ -114,7 +131,7 @@ __device__ __forceinline__ void zero_warp_tile(float* t, int nfloats, int lane) 
 
 // Second loop of the sensor (:105-144) + the dense row of GCA/envs/wrappers.py:130-139: rank the others, (general
 // variant: clip to M, closest_last order), write the lane's observation row into the tile.
-template <int kA, bool kGen>
+template <int kA, bool kGen, bool kAll>
 __device__ __forceinline__ void fast_write_obs_row(const Params& p, const Agent& a, const Ego& e, bool world_ok,
                                                    bool valid, int nm1, int i, int base, const OthersLite<kA>& o,
                                                    float* row, int32_t* sidx_row_in, float* wt, int wt_floats) {
@@ -147,8 +164,8 @@ __device__ __forceinline__ void fast_write_obs_row(const Params& p, const Agent&
   int slot[kNN];
 #pragma unroll
   for (int k = 0; k < kN; ++k) slot[k] = 0;
-  if (kA >= 6) rank_dispatch<kNN, kN>(nm1, key, o.po, slot);
-  else rank_pairs<kNN, kN>(key, o.po, slot);
+  if (kAll) rank_pairs<kNN, kN>(key, o.po, slot);
+  else rank_dispatch<kNN, kN>(nm1, key, o.po, slot);
   // Rows of absent agents and the unused tail of short rows are zeros (wrappers.py:115-139).  A lane clearing its own
   // row serialises against the lanes that have values to write, so when any row of the warp needs zeros all 32 lanes
   // clear the warp's whole tile first with wide stores (ragged batches: ~20 instructions instead of ~300).
@@ -175,7 +192,7 @@ __device__ __forceinline__ void fast_write_obs_row(const Params& p, const Agent&
   const float vxf = (float)a.vx, vyf = (float)a.vy;
 #pragma unroll
   for (int k = 0; k < kN; ++k) {
-    if (kA >= 6 && k >= nm1) continue;   // warp-uniform
+    if (!kAll && k >= nm1) continue;   // warp-uniform
     const int j = k + (k >= i ? 1 : 0);
     const int src = (base + j) & 31;
     const float vxj = __shfl_sync(kFull, vxf, src), vyj = __shfl_sync(kFull, vyf, src);
@@ -191,6 +208,24 @@ __device__ __forceinline__ void fast_write_obs_row(const Params& p, const Agent&
       if (sidx_row) sidx_row[slot[k]] = j;
     }
   }
+}
+
+// Dispatch on "all agents present" (always true for the small specialisations, whose loops are not bounded): the
+// launch-uniform host hint AND the warp's own agent counts, so a stale hint costs speed, never correctness.
+template <int kA, bool kCollide, bool kGen>
+__device__ __forceinline__ void fast_pair_pass_any(const Params& p, const Agent& a, const Ego& e, bool valid, int n, int nm1,
+                                                   int i, int base, OthersLite<kA>& o, bool& coll, double& nearest) {
+  if (kA < 6 || (p.all_present && nm1 == kA - 1)) fast_pair_pass<kA, kCollide, kGen, true>(p, a, e, valid, n, nm1, i, base, o, coll, nearest);
+  else fast_pair_pass<kA, kCollide, kGen, false>(p, a, e, valid, n, nm1, i, base, o, coll, nearest);
+}
+template <int kA, bool kGen>
+__device__ __forceinline__ void fast_write_obs_row_any(const Params& p, const Agent& a, const Ego& e, bool world_ok,
+                                                       bool valid, int nm1, int i, int base, const OthersLite<kA>& o,
+                                                       float* row, int32_t* sidx_row_in, float* wt, int wt_floats) {
+  if (kA < 6 || (p.all_present && nm1 == kA - 1))
+    fast_write_obs_row<kA, kGen, true>(p, a, e, world_ok, valid, nm1, i, base, o, row, sidx_row_in, wt, wt_floats);
+  else
+    fast_write_obs_row<kA, kGen, false>(p, a, e, world_ok, valid, nm1, i, base, o, row, sidx_row_in, wt, wt_floats);
 }
 
 // Warp-level store of the warp's observation rows (its wpw worlds are contiguous in global memory).  The rows were
@@ -303,7 +338,7 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks) ca_step_kernel(const __gri
   bool coll;
   double nearest;
   const int nm1 = others_bound<kA>(n);
-  fast_pair_pass<kA, true, kGen>(p, a, e, valid, n, nm1, i, base, o, coll, nearest);
+  fast_pair_pass_any<kA, true, kGen>(p, a, e, valid, n, nm1, i, base, o, coll, nearest);
 
   // by now this round's own load burst has drained and DRAM is idle while the warps compute
   if (p.prefetch_chunks > 0) prefetch_next_round(p, chunk, wpw, kA, lane);
@@ -322,7 +357,7 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks) ca_step_kernel(const __gri
   // here instead of occupying registers through the ranking / row code.
   if (!__any_sync(kFull, do_reset)) {
     if (valid) store_agent(blk, lane, a, a.policy == CA_POLICY_STATIC, false);
-    fast_write_obs_row<kA, kGen>(p, a, e, world_ok, valid, nm1, i, base, o, row, sidx_row, wtile, (tile_floats + 7) & ~3);
+    fast_write_obs_row_any<kA, kGen>(p, a, e, world_ok, valid, nm1, i, base, o, row, sidx_row, wtile, (tile_floats + 7) & ~3);
   } else {
     // DummyVecEnv semantics: worlds that finished reload their injected initial state and observe again;
     // the other worlds of the warp observe their post-step state.
@@ -339,8 +374,8 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks) ca_step_kernel(const __gri
     bool c_unused;
     double n_unused;
     const int nm1r = others_bound<kA>(n);
-    fast_pair_pass<kA, false, kGen>(p, a, e, valid, n, nm1r, i, base, o, c_unused, n_unused);
-    fast_write_obs_row<kA, kGen>(p, a, e, world_ok, valid, nm1r, i, base, o, row, sidx_row, wtile, (tile_floats + 7) & ~3);
+    fast_pair_pass_any<kA, false, kGen>(p, a, e, valid, n, nm1r, i, base, o, c_unused, n_unused);
+    fast_write_obs_row_any<kA, kGen>(p, a, e, world_ok, valid, nm1r, i, base, o, row, sidx_row, wtile, (tile_floats + 7) & ~3);
   }
 
   CA_STAMP(p, chunk, 4, lane, 0);

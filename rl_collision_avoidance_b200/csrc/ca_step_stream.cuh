@@ -167,7 +167,7 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks) ca_step_stream_kernel(cons
     bool coll;
     double nearest;
     const int nm1 = others_bound<kA>(n);
-    fast_pair_pass<kA, true, kGen>(p, a, e, valid, n, nm1, i, base, o, coll, nearest);
+    fast_pair_pass_any<kA, true, kGen>(p, a, e, valid, n, nm1, i, base, o, coll, nearest);
 
     bool dn, over;
     const float r = step_reward_done<kGen>(p, a, valid, i, coll, nearest, gmask, dn, over);
@@ -194,7 +194,7 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks) ca_step_stream_kernel(cons
     if (!__any_sync(kFull, do_reset)) {
       // state write-back first: heading, time budget, goal and flags die here instead of living through the row code
       if (valid) store_agent(blk, lane, a, a.policy == CA_POLICY_STATIC, false);
-      fast_write_obs_row<kA, kGen>(p, a, e, world_ok, valid, nm1, i, base, o, row, sidx_row, wtile, (tile_floats + 7) & ~3);
+      fast_write_obs_row_any<kA, kGen>(p, a, e, world_ok, valid, nm1, i, base, o, row, sidx_row, wtile, (tile_floats + 7) & ~3);
     } else {
       // DummyVecEnv semantics: worlds that finished reload their snapshot and observe again
       if (do_reset) {
@@ -209,8 +209,8 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks) ca_step_stream_kernel(cons
       bool c_unused;
       double n_unused;
       const int nm1r = others_bound<kA>(n);
-      fast_pair_pass<kA, false, kGen>(p, a, e, valid, n, nm1r, i, base, o, c_unused, n_unused);
-      fast_write_obs_row<kA, kGen>(p, a, e, world_ok, valid, nm1r, i, base, o, row, sidx_row, wtile, (tile_floats + 7) & ~3);
+      fast_pair_pass_any<kA, false, kGen>(p, a, e, valid, n, nm1r, i, base, o, c_unused, n_unused);
+      fast_write_obs_row_any<kA, kGen>(p, a, e, world_ok, valid, nm1r, i, base, o, row, sidx_row, wtile, (tile_floats + 7) & ~3);
     }
 
     if (more) act_next = load_action(nxt);   // an L2 hit by now; consumed after the next chunk's barrier wait
