@@ -58,7 +58,7 @@ RAGGED = False
 ALG_BYTES_PER_AGENT_STEP = 100 + 28 * OTHERS      # 100 + 28*M bytes; 184 B at M = 3, 352 B at M = 9
 WORKLOAD = WORKLOADS["phase1"][3]
 WORKLOAD_NAME = "phase1"
-STATE_BLOCK_BYTES = 2304                           # csrc/ca_kernels.cuh kBlkBytes
+STATE_BLOCK_BYTES = 2560                           # csrc/ca_kernels.cuh kBlkBytes
 FALLBACK_HBM_GBS = 6650.0                          # /opt/skills/guides/B200_PROFILING.md fallback
 
 

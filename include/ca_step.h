@@ -214,10 +214,14 @@ int ca_step_host_wait(ca_env* env);
 int ca_reset_host(ca_env* env, const uint8_t* world_mask, float* obs, int32_t* sorted_idx);
 
 /* Copy the full agent state out: double[W][A][CA_STATE_STRIDE] (device pointer if on_device, else host; host
- * copies synchronise). */
+ * copies synchronise).  CA_S_TIME_REMAINING is rebuilt by repeating the `-= dt` subtractions the agent's steps stand for
+ * from the budget of its last reset (same float64 value as the reference's attribute; budgets of more than 65 534
+ * steps are reported as they were at the reset). */
 int ca_get_state(ca_env* env, double* out, int on_device, void* stream);
 
-/* Time step used by the steps that follow (stream-ordered with them: the value is read when a step is launched).
+/* Time step used by the steps that follow (the value is read when a step is launched).  The library keeps every agent's
+ * time budget as the number of `-= dt` steps it has left, so a call that CHANGES dt recounts them on the device: it
+ * drains the device before and after (no stream argument; not capturable).  A call with the current dt is free.
  * Replaces the per-call `dt` argument of CollisionAvoidanceEnv.step(actions, dt=None)
  * (GCA/envs/collision_avoidance_env.py:131-138; Agent.take_action(action, dt), GCA/envs/agent.py:190).  dt must be > 0. */
 int ca_set_dt(ca_env* env, double dt);

@@ -30,24 +30,37 @@ constexpr unsigned kFull = 0xffffffffu;
 
 // ---- state layout in HBM: chunk-major AoSoA --------------------------------------------------------------------------
 // A "chunk" is what one warp processes: wpw = min(32 / A, 16) whole worlds = wpw * A (<= 32) agent slots, one per lane.
-// All state of a chunk lives in ONE contiguous, 128-byte aligned block of kBlkBytes = 2304 bytes:
-//     double field[8][32]            px py heading time_remaining | gx gy radius pref_speed
-//     uint8  flags[32], policy[32]   per lane
-//     int32  num_agents[16]          per world of the chunk
-//     float  speed[32]               the float32 speed command the agent last executed (0 once it is done)
+// All state of a chunk lives in ONE contiguous, 128-byte aligned block of kBlkBytes = 2560 bytes:
+//     double field[7][32]   px py heading | gx gy radius pref_speed                                   (read by a step)
+//     uint32 meta[32]       flags | policy << 8 | countdown << 16, per lane                           (read by a step)
+//     int32  num_agents[16] per world of the chunk                                                    (read by a step)
+//     float  speed[32]      the float32 speed command the agent last executed (0 once it is done)
+//     double tr0[32]        Agent.time_remaining_to_reach_goal at the last reset
+//     uint32 n0[32]         the countdown at the last reset
 // so a warp reads/writes each field as one coalesced run at a constant offset from a single base pointer, and the part
-// of a block that a step has to fetch (everything but `speed`) is ONE TMA bulk copy of kBlkReadBytes = 2176 bytes
-// (ca_step_stream.cuh).  The reset snapshot uses the same layout in a second buffer.
+// of a block that a step has to fetch is ONE TMA bulk copy of kBlkReadBytes = 1984 bytes (ca_step_stream.cuh).  The
+// reset snapshot uses the same layout in a second buffer.
 // The velocity is not stored: a step writes it as speed * (cos h, sin h) with h the heading it also writes
 // (UnicycleDynamics.step, dynamics/UnicycleDynamics.py:33-34), so the 4-byte command reproduces both float64 components
-// bit for bit (ca_get_state, first observation after a partial reset) and a step moves 12 bytes less per agent.
-constexpr int kFields = 8;
-constexpr int O_PX = 0, O_PY = 32, O_HD = 64, O_TR = 96, O_GX = 128, O_GY = 160, O_RAD = 192, O_PS = 224;
-constexpr int O_TAIL = 256;                     // flags[32] u8, policy[32] u8, num_agents[16] i32
-constexpr int O_SPD = 272;                      // float[32]
-constexpr int kBlkDoubles = kFields * 32 + 16 + 16;  // 288 doubles
-constexpr int kBlkBytes = kBlkDoubles * 8;      // 2304 bytes
-constexpr int kBlkReadBytes = O_SPD * 8;        // 2176 bytes: everything except the speed command
+// bit for bit (ca_get_state, first observation after a partial reset).
+// The time budget is not stored per step either.  The reference subtracts dt from time_remaining_to_reach_goal every
+// step the agent is still running and flags ran_out_of_time when the result is <= 0 (agent.py:232-236); the result of
+// that repeated rounded subtraction has no closed form, but the NUMBER of subtractions until it is <= 0 is fixed once
+// the budget and dt are known.  Whoever writes a budget (unpack_init_kernel, the scenario generator, ca_set_dt) runs the
+// subtractions once (countdown_steps) and a step only decrements a 16-bit countdown that shares a word with the flags:
+// 4 bytes read + written per agent-step instead of 17, the same step at which the flag rises, and ca_get_state rebuilds
+// the float64 value by repeating the (n0 - countdown) subtractions from tr0.
+constexpr int kFields = 7;
+constexpr int O_PX = 0, O_PY = 32, O_HD = 64, O_GX = 96, O_GY = 128, O_RAD = 160, O_PS = 192;
+constexpr int O_META = 224;                     // uint32[32]
+constexpr int O_NAG = 240;                      // int32[16]
+constexpr int O_SPD = 248;                      // float[32]; the read window of a step ends here
+constexpr int O_TR0 = 264;                      // double[32]
+constexpr int O_N0 = 296;                       // uint32[32]
+constexpr int kBlkDoubles = 320;
+constexpr int kBlkBytes = kBlkDoubles * 8;      // 2560 bytes
+constexpr int kBlkReadBytes = O_SPD * 8;        // 1984 bytes
+constexpr unsigned kNever = 0xFFFFu;            // countdown value of a budget that does not run out within 65 534 steps
 
 struct StateBlocks {
   double* base;  // [n_chunks][kBlkDoubles]
@@ -56,10 +69,27 @@ struct StateBlocks {
 __host__ __device__ __forceinline__ int worlds_per_chunk(int A) { return (32 / A) < 16 ? (32 / A) : 16; }
 
 __device__ __forceinline__ double* blk_ptr(const StateBlocks& s, long chunk) { return s.base + chunk * kBlkDoubles; }
-__device__ __forceinline__ uint8_t* blk_flags(double* blk) { return reinterpret_cast<uint8_t*>(blk + O_TAIL); }
-__device__ __forceinline__ uint8_t* blk_policy(double* blk) { return reinterpret_cast<uint8_t*>(blk + O_TAIL) + 32; }
-__device__ __forceinline__ int32_t* blk_nag(double* blk) { return reinterpret_cast<int32_t*>(blk + O_TAIL + 8); }
+__device__ __forceinline__ uint32_t* blk_meta(double* blk) { return reinterpret_cast<uint32_t*>(blk + O_META); }
+__device__ __forceinline__ int32_t* blk_nag(double* blk) { return reinterpret_cast<int32_t*>(blk + O_NAG); }
 __device__ __forceinline__ float* blk_spd(double* blk) { return reinterpret_cast<float*>(blk + O_SPD); }
+__device__ __forceinline__ uint32_t* blk_n0(double* blk) { return reinterpret_cast<uint32_t*>(blk + O_N0); }
+__host__ __device__ __forceinline__ uint32_t pack_meta(unsigned flags, int policy, unsigned cd) {
+  return (flags & 0xffu) | (((unsigned)policy & 0xffu) << 8) | (cd << 16);
+}
+
+// Number of `-= dt` steps after which a time budget tr0 is <= 0 (agent.py:232-236), saturating at kNever.
+__host__ __device__ __forceinline__ unsigned countdown_steps(double tr0, double dt) {
+  double t = tr0;
+  unsigned n = 0;
+  do { t -= dt; ++n; } while (t > 0.0 && n < kNever);
+  return n;
+}
+// The budget after k of those steps.
+__host__ __device__ __forceinline__ double budget_after(double tr0, double dt, unsigned k) {
+  double t = tr0;
+  for (unsigned q = 0; q < k; ++q) t -= dt;
+  return t;
+}
 
 // (world, agent) -> (chunk, lane) for kernels that are not organised warp-per-chunk
 __device__ __forceinline__ void slot_of(int w, int i, int A, long& chunk, int& lane, int& wl) {
@@ -243,9 +273,11 @@ __device__ __forceinline__ bool key_before(int mode, double qa, double pa, doubl
 
 // The per-lane agent record kept in registers.
 struct Agent {
-  double px, py, hd, vx, vy, tr, gx, gy, rad, ps;
-  float spd;  // float32 speed command last executed (what the block stores instead of the velocity)
+  double px, py, hd, vx, vy, gx, gy, rad, ps;
+  double tr0;   // time budget at the last reset: only loaded / stored where a world is (re)set
+  float spd;    // float32 speed command last executed (what the block stores instead of the velocity)
   unsigned flags;
+  unsigned cd;  // steps left until ran_out_of_time (kNever: never)
   int policy;
 };
 
@@ -256,11 +288,13 @@ struct Agent {
 template <bool kVel = true>
 __device__ __forceinline__ void load_agent(const double* blk, int lane, Agent& a) {
   a.px = blk[O_PX + lane]; a.py = blk[O_PY + lane]; a.hd = blk[O_HD + lane];
-  a.tr = blk[O_TR + lane];
   a.gx = blk[O_GX + lane]; a.gy = blk[O_GY + lane]; a.rad = blk[O_RAD + lane];
   a.ps = blk[O_PS + lane];
-  a.flags = blk_flags(const_cast<double*>(blk))[lane];
-  a.policy = blk_policy(const_cast<double*>(blk))[lane];
+  const uint32_t m = blk_meta(const_cast<double*>(blk))[lane];
+  a.flags = m & 0xffu;
+  a.policy = (int)((m >> 8) & 0xffu);
+  a.cd = m >> 16;
+  a.tr0 = 0.0;
   if (kVel) {
     a.spd = blk_spd(const_cast<double*>(blk))[lane];
     a.vx = 0.0; a.vy = 0.0;
@@ -274,19 +308,28 @@ __device__ __forceinline__ void load_agent(const double* blk, int lane, Agent& a
   }
 }
 
-// write-back of one lane: the dynamic fields always, goal / static fields only when they changed
+// a snapshot (or any block a world is (re)set from): the step fields plus the time budget the countdown stands for
+__device__ __forceinline__ void load_agent_reset(const double* blk, int lane, Agent& a) {
+  load_agent<false>(blk, lane, a);
+  a.tr0 = blk[O_TR0 + lane];
+}
+
+// write-back of one lane: the dynamic fields always, goal / static fields only when they changed; all = a world is
+// (re)set: every field, and the countdown as it stands becomes the reference point n0 of the new episode
 __device__ __forceinline__ void store_agent(double* blk, int lane, const Agent& a, bool goal_too, bool all) {
   blk[O_PX + lane] = a.px; blk[O_PY + lane] = a.py; blk[O_HD + lane] = a.hd;
-  blk[O_TR + lane] = a.tr;
   blk_spd(blk)[lane] = a.spd;
-  blk_flags(blk)[lane] = (uint8_t)a.flags;
+  blk_meta(blk)[lane] = pack_meta(a.flags, a.policy, a.cd);
   if (goal_too || all) { blk[O_GX + lane] = a.gx; blk[O_GY + lane] = a.gy; }
-  if (all) { blk[O_RAD + lane] = a.rad; blk[O_PS + lane] = a.ps; blk_policy(blk)[lane] = (uint8_t)a.policy; }
+  if (all) {
+    blk[O_RAD + lane] = a.rad; blk[O_PS + lane] = a.ps;
+    blk[O_TR0 + lane] = a.tr0; blk_n0(blk)[lane] = a.cd;
+  }
 }
 
 __device__ __forceinline__ void zero_agent(Agent& a) {
-  a.px = a.py = a.hd = a.vx = a.vy = a.tr = a.gx = a.gy = a.rad = a.ps = 0.0;
-  a.spd = 0.f; a.flags = 0; a.policy = 0;
+  a.px = a.py = a.hd = a.vx = a.vy = a.gx = a.gy = a.rad = a.ps = a.tr0 = 0.0;
+  a.spd = 0.f; a.flags = 0; a.cd = 0; a.policy = 0;
 }
 
 // ---- the step body shared by every step kernel (generic, one-shot, streaming) ------------------------------------------
@@ -342,8 +385,8 @@ __device__ __forceinline__ void step_take_action(const Params& p, Agent& a, int 
     a.hd = h;
     const double ex = a.px - a.gx, ey = a.py - a.gy;
     if (ex * ex + ey * ey <= p.thr_sq) a.flags |= CA_F_AT_GOAL; else a.flags &= ~CA_F_AT_GOAL;
-    a.tr -= p.dt;
-    if (a.tr <= 0.0) a.flags |= CA_F_RAN_OUT_OF_TIME;
+    if (a.cd != kNever) a.cd -= 1;   // time_remaining_to_reach_goal -= dt ... (agent.py:232-236, see the layout notes)
+    if (a.cd == 0) a.flags |= CA_F_RAN_OUT_OF_TIME;
   }
 }
 
@@ -595,7 +638,7 @@ __global__ void __launch_bounds__(kBlock) ca_world_kernel(const __grid_constant_
       n = blk_nag(blk0)[wl];
       valid = i < n;
       if (i == 0) { blk_nag(blk)[wl] = n; p.consumed[w] = 1; }
-      if (valid) load_agent<false>(blk0, lane, a); else zero_agent(a);  // a snapshot is at rest
+      if (valid) load_agent_reset(blk0, lane, a); else zero_agent(a);  // a snapshot is at rest
       e = ego_frame(a.px, a.py, a.gx, a.gy, a.hd);
     }
     bool c_unused;

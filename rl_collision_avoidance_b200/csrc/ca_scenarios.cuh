@@ -31,6 +31,7 @@ struct ScenarioParams {
   int W, A;
   int only_consumed;
   double dt, thr, max_time_ratio;
+  double step_dt;     // dt of the steps (ca_set_dt): what the time budget is counted down in
   unsigned long long seed, offset;
 };
 
@@ -237,9 +238,10 @@ __global__ void __launch_bounds__(kGenWarps * 32) generate_scenarios_kernel(cons
     blk[O_PX + dst] = live ? ag.px[i] : 0.0; blk[O_PY + dst] = live ? ag.py[i] : 0.0;
     blk[O_GX + dst] = live ? ag.gx[i] : 0.0; blk[O_GY + dst] = live ? ag.gy[i] : 0.0;
     blk[O_HD + dst] = live ? heading : 0.0;
-    blk_spd(blk)[dst] = 0.f; blk[O_TR + dst] = t0;
+    const unsigned cd = live ? countdown_steps(t0, p.step_dt) : 0u;   // the budget as a number of steps (ca_kernels.cuh)
+    blk_spd(blk)[dst] = 0.f; blk[O_TR0 + dst] = t0; blk_n0(blk)[dst] = cd;
     blk[O_RAD + dst] = live ? ag.rd[i] : 0.0; blk[O_PS + dst] = live ? ag.sp[i] : 0.0;
-    blk_flags(blk)[dst] = 0; blk_policy(blk)[dst] = live ? (uint8_t)pol : 0;
+    blk_meta(blk)[dst] = pack_meta(0u, live ? pol : 0, cd);
   }
 }
 

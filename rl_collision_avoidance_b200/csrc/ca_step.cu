@@ -117,7 +117,7 @@ using ca::kWarps;
 // agent.py:29-136.
 __global__ void unpack_init_kernel(const double* __restrict__ init, const int32_t* __restrict__ nag_in, ca::StateBlocks s,
                                    ca::StateBlocks s0, int W, int A, double max_time_ratio, double thr, double dt,
-                                   bool snapshot_only, unsigned* ragged_flag) {
+                                   double step_dt, bool snapshot_only, unsigned* ragged_flag) {
   const long g = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (g >= (long)W * A) return;
   const int w = (int)(g / A), i = (int)(g - (long)w * A);
@@ -144,14 +144,16 @@ __global__ void unpack_init_kernel(const double* __restrict__ init, const int32_
     if (!(t0 > dt)) t0 = dt;
   }
   ca::Agent a;
-  a.px = v[CA_I_PX]; a.py = v[CA_I_PY]; a.hd = v[CA_I_HEADING]; a.vx = 0.0; a.vy = 0.0; a.spd = 0.f; a.tr = i < n ? t0 : 0.0;
+  a.px = v[CA_I_PX]; a.py = v[CA_I_PY]; a.hd = v[CA_I_HEADING]; a.vx = 0.0; a.vy = 0.0; a.spd = 0.f;
+  a.tr0 = i < n ? t0 : 0.0;
+  a.cd = i < n ? ca::countdown_steps(t0, step_dt) : 0u;   // the steps after which the budget is spent (ca_kernels.cuh)
   a.gx = v[CA_I_GX]; a.gy = v[CA_I_GY]; a.rad = v[CA_I_RADIUS]; a.ps = v[CA_I_PREF_SPEED];
   a.flags = 0; a.policy = (int)v[CA_I_POLICY];
   ca::store_agent(b0, lane, a, true, true);
   if (!snapshot_only) ca::store_agent(b, lane, a, true, true);
 }
 
-__global__ void pack_state_kernel(ca::StateBlocks s, double* __restrict__ out, int W, int A) {
+__global__ void pack_state_kernel(ca::StateBlocks s, double* __restrict__ out, int W, int A, double step_dt) {
   const long g = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (g >= (long)W * A) return;
   const int w = (int)(g / A), i = (int)(g - (long)w * A);
@@ -159,11 +161,44 @@ __global__ void pack_state_kernel(ca::StateBlocks s, double* __restrict__ out, i
   int lane, wl;
   ca::slot_of(w, i, A, chunk, lane, wl);
   ca::Agent a;
-  ca::load_agent(ca::blk_ptr(s, chunk), lane, a);
+  double* const blk = ca::blk_ptr(s, chunk);
+  ca::load_agent(blk, lane, a);
+  // time_remaining_to_reach_goal: the subtractions the agent's steps stand for, repeated from the budget of its last reset
+  const unsigned n0 = ca::blk_n0(blk)[lane];
+  const double tr = ca::budget_after(blk[ca::O_TR0 + lane], step_dt, (a.cd == ca::kNever || n0 < a.cd) ? 0u : n0 - a.cd);
   double* r = out + g * CA_STATE_STRIDE;
   r[CA_S_PX] = a.px; r[CA_S_PY] = a.py; r[CA_S_HEADING] = a.hd; r[CA_S_VX] = a.vx; r[CA_S_VY] = a.vy;
-  r[CA_S_TIME_REMAINING] = a.tr; r[CA_S_GX] = a.gx; r[CA_S_GY] = a.gy; r[CA_S_RADIUS] = a.rad;
+  r[CA_S_TIME_REMAINING] = tr; r[CA_S_GX] = a.gx; r[CA_S_GY] = a.gy; r[CA_S_RADIUS] = a.rad;
   r[CA_S_PREF_SPEED] = a.ps; r[CA_S_FLAGS] = (double)a.flags; r[CA_S_POLICY] = (double)a.policy;
+}
+
+// ca_set_dt with a new dt: the countdowns were counted in steps of the old one.  Live agents: the budget they have left
+// (old-dt subtractions from tr0) becomes the new reference point; snapshots: the same budget, recounted.
+__global__ void rebase_countdown_kernel(ca::StateBlocks s, ca::StateBlocks s0, int W, int A, double dt_old, double dt_new) {
+  const long g = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= (long)W * A) return;
+  const int w = (int)(g / A), i = (int)(g - (long)w * A);
+  long chunk;
+  int lane, wl;
+  ca::slot_of(w, i, A, chunk, lane, wl);
+  double* b = ca::blk_ptr(s, chunk);
+  double* b0 = ca::blk_ptr(s0, chunk);
+  {
+    const uint32_t m = ca::blk_meta(b)[lane];
+    const unsigned cd = m >> 16, n0 = ca::blk_n0(b)[lane];
+    const double left = ca::budget_after(b[ca::O_TR0 + lane], dt_old, (cd == ca::kNever || n0 < cd) ? 0u : n0 - cd);
+    // an agent whose budget is spent (cd == 0) stays there; an absent slot (n0 == 0, cd == 0) too
+    const unsigned ncd = cd == 0 ? 0u : ca::countdown_steps(left, dt_new);
+    b[ca::O_TR0 + lane] = left;
+    ca::blk_n0(b)[lane] = ncd;
+    ca::blk_meta(b)[lane] = (m & 0xffffu) | (ncd << 16);
+  }
+  {
+    const uint32_t m = ca::blk_meta(b0)[lane];
+    const unsigned ncd = (m >> 16) == 0 ? 0u : ca::countdown_steps(b0[ca::O_TR0 + lane], dt_new);
+    ca::blk_n0(b0)[lane] = ncd;
+    ca::blk_meta(b0)[lane] = (m & 0xffffu) | (ncd << 16);
+  }
 }
 
 void carve(ca_env* e) {
@@ -577,7 +612,7 @@ static int set_state_impl(ca_env* e, const double* init, const int32_t* num_agen
   unsigned* const ragged_flag = e->ticket + 16;   // a spare word of the handle's 128-byte counter block
   if (on_device) CA_CUDA(cudaMemsetAsync(ragged_flag, 0, sizeof(unsigned), st));
   unpack_init_kernel<<<blocks, threads, 0, st>>>(d_init, d_nag, e->s, e->s0, e->W, e->A, e->cfg.max_time_ratio,
-                                                 e->cfg.near_goal_threshold, e->cfg.dt, snapshot_only, ragged_flag);
+                                                 e->cfg.near_goal_threshold, e->cfg.dt, e->step_dt, snapshot_only, ragged_flag);
   CA_CUDA(cudaPeekAtLastError());
   e->launches += 1;
   if (on_device) {   // device-resident counts: the kernel reports whether every world has all A agents
@@ -698,7 +733,7 @@ int ca_get_state(ca_env* e, double* out, int on_device, void* stream) {
     d_out = e->d_boundary;
   }
   const int threads = 256;
-  pack_state_kernel<<<(int)((n + threads - 1) / threads), threads, 0, st>>>(e->s, d_out, e->W, e->A);
+  pack_state_kernel<<<(int)((n + threads - 1) / threads), threads, 0, st>>>(e->s, d_out, e->W, e->A, e->step_dt);
   CA_CUDA(cudaPeekAtLastError());
   e->launches += 1;
   if (!on_device) {
@@ -711,6 +746,17 @@ int ca_get_state(ca_env* e, double* out, int on_device, void* stream) {
 int ca_set_dt(ca_env* e, double dt) {
   if (!e) return fail(CA_ERR_INVALID_ARG, "NULL argument");
   if (!(dt > 0) || !std::isfinite(dt)) return fail(CA_ERR_INVALID_ARG, "dt must be > 0");
+  if (dt != e->step_dt && e->initialised) {
+    // the time budgets are kept as step countdowns (ca_kernels.cuh): recount them for the new step length.  No stream
+    // argument in this entry point: the device is drained on both sides of the recount.
+    DeviceGuard guard(e->cfg.device);
+    CA_CUDA(cudaDeviceSynchronize());
+    const long n = (long)e->W * e->A;
+    rebase_countdown_kernel<<<(int)((n + 255) / 256), 256>>>(e->s, e->s0, e->W, e->A, e->step_dt, dt);
+    CA_CUDA(cudaPeekAtLastError());
+    CA_CUDA(cudaDeviceSynchronize());
+    e->launches += 1;
+  }
   e->step_dt = dt;   // make_params() copies it into the next launch's parameters; Config.DT (reset time budget) stays
   return CA_OK;
 }
@@ -771,6 +817,7 @@ int ca_generate_scenarios(ca_env* e, const ca_scenario_config* c, uint64_t seed,
   memset(&p, 0, sizeof(p));
   p.c = *c; p.s0 = e->s0; p.consumed = e->consumed; p.W = e->W; p.A = e->A;
   p.only_consumed = only_consumed; p.dt = e->cfg.dt; p.thr = e->cfg.near_goal_threshold;
+  p.step_dt = e->step_dt;
   p.max_time_ratio = e->cfg.max_time_ratio; p.seed = seed; p.offset = e->gen_calls * 4096ull;
   e->gen_calls += 1;
   ca::generate_scenarios_kernel<<<(e->W + ca::kGenWarps - 1) / ca::kGenWarps, ca::kGenWarps * 32, 0, (cudaStream_t)stream>>>(p);

@@ -366,7 +366,7 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks) ca_step_kernel(const __gri
       n = blk_nag(blk0)[wl];
       valid = i < n;
       if (i == 0) { blk_nag(blk)[wl] = n; p.consumed[w] = 1; }
-      if (valid) load_agent<false>(blk0, lane, a); else zero_agent(a);  // a snapshot is at rest
+      if (valid) load_agent_reset(blk0, lane, a); else zero_agent(a);  // a snapshot is at rest
       e = ego_frame(a.px, a.py, a.gx, a.gy, a.hd);
     }
     if (valid || do_reset)  // a reset rewrites every slot of the world (the new scenario may have fewer agents)

@@ -202,7 +202,7 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks) ca_step_stream_kernel(cons
         n = blk_nag(blk0)[wl];
         valid = i < n;
         if (i == 0) { blk_nag(blk)[wl] = n; p.consumed[w] = 1; }
-        if (valid) load_agent<false>(blk0, lane, a); else zero_agent(a);  // a snapshot is at rest
+        if (valid) load_agent_reset(blk0, lane, a); else zero_agent(a);  // a snapshot is at rest
         e = ego_frame(a.px, a.py, a.gx, a.gy, a.hd);
       }
       if (valid || do_reset) store_agent(blk, lane, a, a.policy == CA_POLICY_STATIC, do_reset);
