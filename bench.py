@@ -291,7 +291,9 @@ class GraphedSteps(object):
             main = self.stream
             g = torch.cuda.CUDAGraph()
             with torch.cuda.stream(main):
-                with torch.cuda.graph(g, stream=main):
+                # thread-local capture mode: CUDA calls of OTHER threads (the NCCL watchdog polling its events) must not
+                # invalidate a capture of a few thousand launches
+                with torch.cuda.graph(g, stream=main, capture_error_mode="thread_local"):
                     fork = torch.cuda.Event()
                     fork.record(main)
                     for st in self.streams[1:S]:
@@ -335,8 +337,9 @@ class GraphedSteps(object):
         self.torch.cuda.empty_cache()
 
 
-def env_workload_record(name, rank, local_rank, steps, barrier, max_over_ranks, world_size, streams):
-    """One extra env.step workload (device-resident, same method as `value`): a sub-record with its own roofline."""
+def env_workload_record(name, rank, local_rank, steps, streams):
+    """One extra env.step workload (device-resident, same method as `value`).  Rank-local: returns the two timings to be
+    max-reduced over ranks and a function that builds the sub-record (with its own roofline) from the reduced values."""
     saved = WORKLOAD_NAME
     select_workload(name)
     try:
@@ -344,29 +347,34 @@ def env_workload_record(name, rank, local_rank, steps, barrier, max_over_ranks, 
         gs = GraphedSteps(sets, local_rank, 4321 + rank, streams=streams)
         gs.run(2 * gs.G)
         gs.run(steps)
-        ms = max_over_ranks(gs.run(steps, barrier))
+        ms = gs.run(steps)
         gs.run(steps, streams=1)
-        ms1 = max_over_ranks(gs.run(steps, barrier, streams=1))
+        ms1 = gs.run(steps, streams=1)
         S = gs.S
         gs.close()
         live = live_agents(WORLDS_PER_GPU)
-        peak, _ = measured_peak()
-        launch_ms = ms / steps
-        achieved = ALG_BYTES_PER_AGENT_STEP * live / (launch_ms * 1e-3) / 1e9
-        achieved1 = ALG_BYTES_PER_AGENT_STEP * live / (ms1 / steps * 1e-3) / 1e9
-        return {"workload": WORKLOAD, "value": world_size * live * steps / (ms * 1e-3), "unit": "agent-steps/s",
-                "ms_per_step": launch_ms, "steps": steps, "streams": S, "worlds_per_gpu": WORLDS_PER_GPU, "agent_slots": AGENTS,
-                "live_agents_per_step": live,
-                "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                             "algorithmic_bytes_per_launch": ALG_BYTES_PER_AGENT_STEP * live,
-                             "traffic": ncu_traffic_per_launch(name), "kernel": step_kernel_name()},
-                "single_stream": {"value": world_size * live * steps / (ms1 * 1e-3), "ms_per_step": ms1 / steps,
-                                  "roofline_frac": achieved1 / peak}}
+        alg, worlds, agents, text = ALG_BYTES_PER_AGENT_STEP, WORLDS_PER_GPU, AGENTS, WORKLOAD
+        kernel, traffic = step_kernel_name(), ncu_traffic_per_launch(name)
     finally:
         select_workload(saved)
 
+    def finish(vals, world_size):
+        ms, ms1 = vals
+        peak, _ = measured_peak()
+        launch_ms = ms / steps
+        achieved = alg * live / (launch_ms * 1e-3) / 1e9
+        achieved1 = alg * live / (ms1 / steps * 1e-3) / 1e9
+        return {"workload": text, "value": world_size * live * steps / (ms * 1e-3), "unit": "agent-steps/s",
+                "ms_per_step": launch_ms, "steps": steps, "streams": S, "worlds_per_gpu": worlds, "agent_slots": agents,
+                "live_agents_per_step": live,
+                "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                             "algorithmic_bytes_per_launch": alg * live, "traffic": traffic, "kernel": kernel},
+                "single_stream": {"value": world_size * live * steps / (ms1 * 1e-3), "ms_per_step": ms1 / steps,
+                                  "roofline_frac": achieved1 / peak}}
+    return [ms, ms1], finish
 
-def rollout_record(cls, worlds, steps, fixed_agents, local_rank, max_over_ranks, world_size):
+
+def rollout_record(cls, worlds, steps, fixed_agents, local_rank):
     """BASELINE configs[2]: the GA3C actor -> predictor loop on the device (row plan, fused NetworkVP forward + action
     sampling, env step, statistics, experience bookkeeping, row gather, scenario refresh), random-init weights."""
     import torch
@@ -404,19 +412,23 @@ def rollout_record(cls, worlds, steps, fixed_agents, local_rank, max_over_ranks,
                 rows += int(ro.rec.take()[0].shape[0])
         ev1.record()
         torch.cuda.synchronize()
-        ms = max_over_ranks(ev0.elapsed_time(ev1))
+        ms = ev0.elapsed_time(ev1)
         o = ro.rec.obs_slot(ro.t)
         live = 0.5 * (live + float((o[..., 5] > 0).sum()))
         learning = 0.5 * (learning + float((o[..., 0] != 0).sum()))
         ro.close()
+    finally:
+        cfgmod.set_config(None)
+
+    def finish(vals, world_size):
+        ms = vals[0]
         return {"workload": "%s GA3C rollout, %d worlds x %d agent slots per GPU, %s, fused tcgen05 predictor "
                             "(BASELINE configs[2])" % (cls, worlds, A, "all agents present" if fixed_agents else
                                                        "training mix (2..A agents, 5/90/5 policies)"),
                 "value": world_size * live * steps / (ms * 1e-3), "unit": "live agent-steps/s", "ms_per_step": ms / steps,
                 "steps": steps, "live_agents_per_step": live, "learning_agents_per_step": learning,
                 "training_rows_per_s": world_size * rows / (ms * 1e-3)}
-    finally:
-        cfgmod.set_config(None)
+    return [ms], finish
 
 
 def train_loop_record(seconds, worlds, local_rank, world_size):
@@ -472,7 +484,9 @@ def run_ours(args):
     distributed = world_size > 1
     if distributed:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        import datetime
+        # a rank that dies must not hold the others (and the box) for the default 10 minutes
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank), timeout=datetime.timedelta(seconds=180))
 
     def barrier():
         if distributed:
@@ -557,17 +571,37 @@ def run_ours(args):
     # ---- extra workloads (sub-records; every rank takes part so that N > 1 numbers are whole-job numbers)
     extras = {}
     if not args.no_extras and WORKLOAD_NAME == "phase1":
-        def guarded(key, fn):
+        def reduced(key, n_vals, fn):
+            """Rank-local measurement + EXACTLY ONE collective per extra whatever happens on a rank: [failed, timings...]
+            max-reduced over ranks, so an exception on one rank can neither deadlock the others nor shift the sequence
+            of collectives; the sub-record is built from the reduced timings (or reports the failure)."""
+            vals, finish, err = [0.0] * n_vals, None, None
             try:
-                extras[key] = fn()
+                vals, finish = fn()
             except Exception as e:   # an extra record must never take the headline down
-                extras[key] = {"error": repr(e)}
-            barrier()
-        guarded("phase2_env_step", lambda: env_workload_record("phase2", rank, local_rank, 240, barrier, max_over_ranks, world_size, S))
-        guarded("ragged_env_step", lambda: env_workload_record("ragged", rank, local_rank, 240, barrier, max_over_ranks, world_size, S))
-        guarded("rollout_phase2_all_present", lambda: rollout_record("TrainPhase2", 16384, 96, True, local_rank, max_over_ranks, world_size))
-        guarded("rollout_phase2_training_mix", lambda: rollout_record("TrainPhase2", 16384, 96, False, local_rank, max_over_ranks, world_size))
-        guarded("train_loop", lambda: train_loop_record(args.train_seconds, 65536, local_rank, world_size))
+                err = repr(e)
+                print("[bench] extra workload %s failed on rank %d: %s" % (key, rank, err), file=sys.stderr, flush=True)
+            t = torch.tensor([1.0 if err else 0.0] + [float(v) for v in vals], dtype=torch.float64, device="cuda")
+            if distributed:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            t = t.tolist()
+            if t[0] != 0.0 or finish is None:
+                extras[key] = {"error": err or "failed on another rank"}
+            else:
+                extras[key] = finish(t[1:], world_size)
+        reduced("phase2_env_step", 2, lambda: env_workload_record("phase2", rank, local_rank, 240, S))
+        reduced("ragged_env_step", 2, lambda: env_workload_record("ragged", rank, local_rank, 240, S))
+        reduced("rollout_phase2_all_present", 1, lambda: rollout_record("TrainPhase2", 16384, 96, True, local_rank))
+        reduced("rollout_phase2_training_mix", 1, lambda: rollout_record("TrainPhase2", 16384, 96, False, local_rank))
+        # the training loop has collectives of its own (gradient all-reduce): every rank must enter it, and a rank-local
+        # failure inside it cannot be isolated — the process group's timeout bounds the damage
+        barrier()
+        try:
+            extras["train_loop"] = train_loop_record(args.train_seconds, 65536, local_rank, world_size)
+        except Exception as e:
+            extras["train_loop"] = {"error": repr(e)}
+            print("[bench] train_loop failed on rank %d: %r" % (rank, e), file=sys.stderr, flush=True)
+        barrier()
     clocks = sampler.stop()
 
     if rank == 0:

@@ -261,14 +261,14 @@ class GraphedTrainStep(object):
                 self._update_body()
             side.synchronize()
             self.g_bwd = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(self.g_bwd, stream=side):
+            with torch.cuda.graph(self.g_bwd, stream=side, capture_error_mode="thread_local"):
                 self._backward_body()
                 if allreduce is None:
                     self._update_body()
             self.g_upd = None
             if allreduce is not None:
                 self.g_upd = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(self.g_upd, stream=side):
+                with torch.cuda.graph(self.g_upd, stream=side, capture_error_mode="thread_local"):
                     self._update_body()
         torch.cuda.current_stream(dev).wait_stream(side)
         with torch.no_grad():   # the warm-up steps must not count
