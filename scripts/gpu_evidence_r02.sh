@@ -14,5 +14,8 @@ for wl in phase1 phase2 ragged; do
 timeout 600 ncu --cache-control none --clock-control none --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum,lts__t_bytes.sum -k regex:ca_step_kernel -s 36 -c 24 --csv --log-file gpurun_out/r02_traffic_$wl.csv python bench.py --workload $wl --steps 96 --warmup 12 --no-cpu-baseline --no-extras --streams 1 > gpurun_out/r02_ncu_traffic_$wl.log 2>&1
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:ca_step_kernel -s 40 -c 1 -o gpurun_out/r02c_step_$wl -f python bench.py --workload $wl --steps 96 --warmup 12 --no-cpu-baseline --no-extras --streams 1 > gpurun_out/r02_ncu_full_$wl.log 2>&1
 done
+if [ -n "$CA_EVIDENCE_PREDICTOR" ]; then
 timeout 300 ncu --set full --clock-control none --import-source on -k regex:predict_kernel -s 2 -c 1 -o gpurun_out/r02c_predict -f python scripts/predict_probe.py one 9 163840 0 > gpurun_out/r02_ncu_predict.log 2>&1
+fi
+timeout 300 python scripts/step_sweep.py phase1: phase1:_STREAMS=3 phase2: phase2:_STREAMS=3 ragged: ragged:_STREAMS=3 > gpurun_out/r02_sweep_final.log 2>&1
 tail -2 gpurun_out/r02_smoke.log; tail -3 gpurun_out/r02_pytest_gpu.log; cut -c1-300 gpurun_out/r02_bench.json
