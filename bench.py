@@ -318,9 +318,10 @@ class GraphedSteps(object):
             if barrier:
                 barrier()
             ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            # ~0.2 ms of device-side spinning first, so that the events and the graph launch are all enqueued before the
-            # device reaches them: no host latency lands inside the timed region, however short it is (--steps 20)
-            torch.cuda._sleep(400000)
+            # device-side spinning first (~0.2 ms + ~1 us per captured launch: submitting a graph of a few thousand nodes
+            # takes the host about that long), so that the events and the graph launch are all enqueued before the device
+            # reaches them: no host latency lands inside the timed region, however short it is (--steps 20)
+            torch.cuda._sleep(400000 + 2000 * int(steps))
             ev0.record(self.stream)
             g.replay()
             ev1.record(self.stream)
