@@ -360,16 +360,28 @@ int launch_world_kernel(ca_env* e, bool step, ca::Params& p, cudaStream_t st) {
 int ensure_staging(ca_env* e) {
   if (e->hstream) return CA_OK;
   const size_t n = (size_t)e->W * e->A;
-  CA_CUDA(cudaStreamCreateWithFlags(&e->hstream, cudaStreamNonBlocking));
-  CA_CUDA(cudaMalloc(&e->d_actions, n * sizeof(int32_t)));
-  CA_CUDA(cudaMalloc(&e->d_cont, n * 2 * sizeof(double)));
-  CA_CUDA(cudaMalloc(&e->d_obs, n * e->L * sizeof(float)));
-  CA_CUDA(cudaMalloc(&e->d_reward, n * sizeof(float)));
-  CA_CUDA(cudaMalloc(&e->d_done, n));
-  CA_CUDA(cudaMalloc(&e->d_over, (size_t)e->W));
-  CA_CUDA(cudaMalloc(&e->d_mask, (size_t)e->W));
-  CA_CUDA(cudaMalloc(&e->d_sidx, n * e->M * sizeof(int32_t)));
-  CA_CUDA(cudaMemsetAsync(e->d_actions, 0, n * sizeof(int32_t), e->hstream));
+  cudaStream_t st = nullptr;
+  CA_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+  // all or nothing: hstream (the "staging is ready" marker) is only set once every buffer exists
+  const bool ok = cudaMalloc(&e->d_actions, n * sizeof(int32_t)) == cudaSuccess &&
+                  cudaMalloc(&e->d_cont, n * 2 * sizeof(double)) == cudaSuccess &&
+                  cudaMalloc(&e->d_obs, n * e->L * sizeof(float)) == cudaSuccess &&
+                  cudaMalloc(&e->d_reward, n * sizeof(float)) == cudaSuccess &&
+                  cudaMalloc(&e->d_done, n) == cudaSuccess &&
+                  cudaMalloc(&e->d_over, (size_t)e->W) == cudaSuccess &&
+                  cudaMalloc(&e->d_mask, (size_t)e->W) == cudaSuccess &&
+                  cudaMalloc(&e->d_sidx, n * e->M * sizeof(int32_t)) == cudaSuccess &&
+                  cudaMemsetAsync(e->d_actions, 0, n * sizeof(int32_t), st) == cudaSuccess;
+  if (!ok) {
+    cudaFree(e->d_actions); cudaFree(e->d_cont); cudaFree(e->d_obs); cudaFree(e->d_reward);
+    cudaFree(e->d_done); cudaFree(e->d_over); cudaFree(e->d_mask); cudaFree(e->d_sidx);
+    e->d_actions = nullptr; e->d_cont = nullptr; e->d_obs = nullptr; e->d_reward = nullptr;
+    e->d_done = nullptr; e->d_over = nullptr; e->d_mask = nullptr; e->d_sidx = nullptr;
+    cudaStreamDestroy(st);
+    cudaGetLastError();
+    return fail(CA_ERR_ALLOC, "cudaMalloc of the host-path staging buffers failed");
+  }
+  e->hstream = st;
   return CA_OK;
 }
 
