@@ -592,6 +592,9 @@ int ca_destroy(ca_env* e) {
   cudaFree(e->d_actions); cudaFree(e->d_cont); cudaFree(e->d_obs); cudaFree(e->d_reward);
   cudaFree(e->d_done); cudaFree(e->d_over); cudaFree(e->d_mask); cudaFree(e->d_sidx);
   cudaFree(e->d_boundary); cudaFree(e->d_boundary_nag);
+#ifdef CA_TRACE
+  cudaFree(e->trace);
+#endif
   if (e->hstream) cudaStreamDestroy(e->hstream);
   delete e;
   return CA_OK;
