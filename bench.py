@@ -432,6 +432,29 @@ def rollout_record(cls, worlds, steps, fixed_agents, local_rank):
     return [ms], finish
 
 
+def reduce_extra(key, n_vals, fn, rank, world_size, device, distributed):
+    """One extra workload: a rank-local measurement fn() -> (values, finish) followed by EXACTLY ONE collective whatever
+    happens on a rank — [failed, values...] max-reduced over ranks — so an exception on one rank can neither deadlock the
+    others nor shift the sequence of collectives (the 8-GPU hang of this round: two ranks skipped the six collectives of
+    an extra and paired their later ones with the wrong peers).  Returns finish(reduced values, world_size), or an
+    {"error": ...} record on every rank when any rank failed."""
+    import torch
+    import torch.distributed as dist
+    vals, finish, err = [0.0] * n_vals, None, None
+    try:
+        vals, finish = fn()
+    except Exception as e:   # an extra record must never take the headline down
+        err = repr(e)
+        print("[bench] extra workload %s failed on rank %d: %s" % (key, rank, err), file=sys.stderr, flush=True)
+    t = torch.tensor([1.0 if err else 0.0] + [float(v) for v in vals][:n_vals], dtype=torch.float64, device=device)
+    if distributed:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    t = t.tolist()
+    if t[0] != 0.0 or finish is None:
+        return {"error": err or "failed on another rank"}
+    return finish(t[1:], world_size)
+
+
 def train_loop_record(seconds, worlds, local_rank, world_size):
     """BASELINE configs[4] on this rank count: Server.main (TrainPhase1) with `worlds` worlds per GPU — rollout, A3C
     updates, and (N > 1) the gradient all-reduce over NCCL."""
@@ -573,23 +596,7 @@ def run_ours(args):
     extras = {}
     if not args.no_extras and WORKLOAD_NAME == "phase1":
         def reduced(key, n_vals, fn):
-            """Rank-local measurement + EXACTLY ONE collective per extra whatever happens on a rank: [failed, timings...]
-            max-reduced over ranks, so an exception on one rank can neither deadlock the others nor shift the sequence
-            of collectives; the sub-record is built from the reduced timings (or reports the failure)."""
-            vals, finish, err = [0.0] * n_vals, None, None
-            try:
-                vals, finish = fn()
-            except Exception as e:   # an extra record must never take the headline down
-                err = repr(e)
-                print("[bench] extra workload %s failed on rank %d: %s" % (key, rank, err), file=sys.stderr, flush=True)
-            t = torch.tensor([1.0 if err else 0.0] + [float(v) for v in vals], dtype=torch.float64, device="cuda")
-            if distributed:
-                dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            t = t.tolist()
-            if t[0] != 0.0 or finish is None:
-                extras[key] = {"error": err or "failed on another rank"}
-            else:
-                extras[key] = finish(t[1:], world_size)
+            extras[key] = reduce_extra(key, n_vals, fn, rank, world_size, "cuda", distributed)
         reduced("phase2_env_step", 2, lambda: env_workload_record("phase2", rank, local_rank, 240, S))
         reduced("ragged_env_step", 2, lambda: env_workload_record("ragged", rank, local_rank, 240, S))
         reduced("rollout_phase2_all_present", 1, lambda: rollout_record("TrainPhase2", 16384, 96, True, local_rank))

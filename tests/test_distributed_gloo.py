@@ -83,6 +83,43 @@ def test_two_rank_gloo(tmp_path):
     assert os.path.exists(tmp_path / "ok0") and os.path.exists(tmp_path / "ok1")
 
 
+def _extras_worker(rank, world_size, port, tmpdir):
+    sys.path.insert(0, REPO)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    import torch.distributed as dist
+    dist.init_process_group("gloo", rank=rank, world_size=world_size)
+    import bench
+
+    def measure(ms):
+        return lambda: ([ms, 2 * ms], lambda v, ws: {"ms": v[0], "ms1": v[1], "ranks": ws})
+
+    def broken():
+        raise RuntimeError("capture invalidated")
+
+    # (1) healthy: the slowest rank's timings, on every rank
+    r1 = bench.reduce_extra("a", 2, measure(1.0 + rank), rank, world_size, "cpu", True)
+    assert r1 == {"ms": 2.0, "ms1": 4.0, "ranks": 2}
+    # (2) rank 1 fails before producing anything: BOTH ranks report the failure and nobody hangs ...
+    r2 = bench.reduce_extra("b", 2, broken if rank == 1 else measure(1.0), rank, world_size, "cpu", True)
+    assert "error" in r2
+    # (3) ... and the sequence of collectives is still aligned: the next extra pairs with its peer's
+    r3 = bench.reduce_extra("c", 1, lambda: ([5.0 + rank], lambda v, ws: {"ms": v[0]}), rank, world_size, "cpu", True)
+    assert r3 == {"ms": 6.0}
+    t = torch.tensor([float(rank)])
+    dist.all_reduce(t)
+    assert float(t) == 1.0
+    dist.destroy_process_group()
+    open(os.path.join(tmpdir, "extras_ok%d" % rank), "w").write("ok")
+
+
+def test_bench_extras_survive_a_failing_rank(tmp_path):
+    """bench.py's extra workloads at N > 1: one collective per extra on every rank, whether its measurement worked or not."""
+    port = _free_port()
+    mp.spawn(_extras_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    assert os.path.exists(tmp_path / "extras_ok0") and os.path.exists(tmp_path / "extras_ok1")
+
+
 def test_shard_range_is_a_partition():
     from rl_collision_avoidance_b200.ga3c.parallel import shard_range
     for W, G in ((65536, 8), (10, 3), (7, 8), (524288, 8), (1, 1)):
